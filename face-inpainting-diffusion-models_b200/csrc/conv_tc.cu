@@ -1,0 +1,432 @@
+// K1: 3x3 / 1x1 convolution as implicit GEMM on the 5th-generation tensor cores (tcgen05).
+//
+//   D[M = B*H*W pixels, N = Cout] = sum over taps (r,s) and 64-channel slices of
+//                                   A_{r,s}[M, 64] * W[N, (r,s), 64]^T         (bf16 x bf16 -> fp32)
+//
+// Replaces cuDNN's implicit-GEMM behind every conv_nd of the reference (nn.py:102,153,176,182,184,
+// 252,254; unet.py:55,151).  Design:
+//   * An M tile is a TW x TH x TN box of output pixels (TW*TH*TN = 128).  For tap (r,s) the A operand
+//     is the same box of the NHWC input shifted by (r-1, s-1); one 4-D TMA box load fetches it, the
+//     hardware zero-fills the out-of-image halo (= the conv's zero padding) and writes 128 rows of
+//     64 bf16 with the 128-byte swizzle -- exactly the canonical K-major UMMA operand.  No im2col
+//     buffer ever exists.
+//   * The weight slice [BLOCK_N][64] for (tap, channel slice) is a 2-D TMA box of the KRSC matrix.
+//   * warp 4 = TMA producer, warp 5 = MMA issuer (one thread issues tcgen05.mma, accumulators live in
+//     TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
+//     warps 0-3 = epilogue: tcgen05.ld (one pixel row per thread) -> + bias[c] + emb[n][c]
+//     + residual -> bf16 -> swizzled smem -> TMA store (zero-copy into channel slices of concat
+//     buffers through the tensor map strides), or fp32 NCHW stores for the 6-channel head.
+//   * An optional second (activation, weight) pair is accumulated as extra K iterations: the 1x1
+//     skip_connection of channel-changing ResBlocks (nn.py:184,212) costs no extra pass.
+//   * Persistent CTAs (one per SM), static tile striding; tiles that share an M box are adjacent
+//     so their A boxes hit L2.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sm100_primitives.cuh"
+
+namespace fidm {
+using namespace sm100;
+
+struct ConvTcParams {
+  int B, H, W;             // output == input spatial size (stride 1)
+  int TW, TH, TN;          // pixel box of one M tile
+  int tiles_w, tiles_h, tiles_n;
+  int n_blocks;            // Cout / BLOCK_N
+  int ksize, kc1, cin1;    // taps = ksize^2, kc1 = Cin/64
+  int kc2;                 // Cin2/64 (0: no second source)
+  const float* bias;
+  const float* row_add; int ld_row_add;
+  const __nv_bfloat16* residual; int ld_res;
+  float* y_nchw; int cout_valid;   // non-null: fp32 NCHW output of the first cout_valid channels
+};
+
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;                 // 128 rows x 64 bf16
+constexpr int kStagingBytes = 128 * 128;           // one 128 x 64 bf16 output chunk
+
+template <int BLOCK_N> struct ConvCfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + (kBBytes < 1024 ? 1024 : kBBytes);
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 256 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmY, const ConvTcParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.ksize * p.ksize;
+  const int k_iters = taps * p.kc1 + p.kc2;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_blocks;
+  const int pad = p.ksize >> 1;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    if (!p.y_nchw) tma_prefetch_desc(&tmY);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_blocks, m_blk = tile / p.n_blocks;
+        const int w0 = (m_blk % p.tiles_w) * p.TW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
+        const int co0 = n_blk * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kABytes + Cfg::kBBytes);
+          if (it < taps * p.kc1) {
+            const int tap = it / p.kc1, kc = it - tap * p.kc1;
+            const int r = tap / p.ksize, s = tap - r * p.ksize;
+            tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
+            tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+          } else {
+            const int kc = it - taps * p.kc1;
+            tma_load_4d(&tmA2, &full_bar[stage], sa, kc * 64, w0, h0, n0);
+            tma_load_2d(&tmB2, &full_bar[stage], sb, kc * 64, co0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle atom
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 0-3)
+    const int row = warp * 32 + lane;                 // TMEM lane == pixel row of the tile
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+    const bool issuer = (threadIdx.x == 0);
+    int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_blocks, m_blk = tile / p.n_blocks;
+      const int w0 = (m_blk % p.tiles_w) * p.TW;
+      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
+      const int co0 = n_blk * BLOCK_N;
+      const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+      const bool valid = n < p.B;
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
+
+      if constexpr (BLOCK_N >= 64) {
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_acc + ch * 64, v0);
+          tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
+          tc_wait_ld();
+          if (ch == BLOCK_N / 64 - 1) {       // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          const int cbase = co0 + ch * 64;
+          float f[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 t = __ldg(b4 + j);
+              f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+            }
+          }
+          if (p.row_add && valid) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.row_add + (long long)n * p.ld_row_add + cbase);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 t = __ldg(r4 + j);
+              f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+            }
+          }
+          if (p.residual && valid) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + cbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 t = __ldg(r + j);
+              const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[8 * j + 2 * q] += __uint_as_float(u[q] << 16);
+                f[8 * j + 2 * q + 1] += __uint_as_float(u[q] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (p.y_nchw) {
+            if (valid) {
+              const long long hw = (long long)p.H * p.W;
+              float* o = p.y_nchw + ((long long)n * p.cout_valid) * hw + (long long)h * p.W + w;
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (cbase + j < p.cout_valid) o[(long long)(cbase + j) * hw] = f[j];
+            }
+          } else {
+            // staging buffer `sbuf` was last read by the TMA store issued two chunks ago
+            if (issuer) bulk_wait_group_read<1>();
+            named_bar_sync(1, kEpiWarps * 32);
+            uint8_t* srow = staging + sbuf * kStagingBytes + row * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * u + 0], f[8 * u + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * u + 2], f[8 * u + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * u + 4], f[8 * u + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * u + 6], f[8 * u + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&b0);
+              pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2);
+              pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(srow + ((u ^ (row & 7)) << 4)) = pk;   // 128-byte swizzle
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, kEpiWarps * 32);
+            if (issuer) {
+              tma_store_4d(&tmY, staging + sbuf * kStagingBytes, cbase, w0, h0, n0);
+              bulk_commit_group();
+            }
+            sbuf ^= 1;
+          }
+        }
+      } else {
+        // BLOCK_N == 16: narrow head (out.2, 6 of 16 channels), fp32 NCHW output only
+        uint32_t v[16];
+        tmem_ld_32x16(t_acc, v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (valid && p.y_nchw) {
+          const long long hw = (long long)p.H * p.W;
+          float* o = p.y_nchw + ((long long)n * p.cout_valid) * hw + (long long)h * p.W + w;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = co0 + j;
+            if (c < p.cout_valid) {
+              float val = __uint_as_float(v[j]);
+              if (p.bias) val += __ldg(p.bias + c);
+              if (p.row_add) val += __ldg(p.row_add + (long long)n * p.ld_row_add + c);
+              o[(long long)c * hw] = val;
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 tensor [N][H][W][C] (pixel stride ld elements) as a 4-D map, box = {64, bw, bh, bn}.
+int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode_tiled();
+  FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FIDM_REQUIRE(r == CUDA_SUCCESS, FIDM_E_DRIVER, "cuTensorMapEncodeTiled(NHWC C=%d W=%d H=%d N=%d ld=%d box=%d,%d,%d) failed: %d",
+               C, W, H, N, ld, bw, bh, bn, (int)r);
+  return 0;
+}
+
+// Row-major bf16 matrix [rows][cols] (row stride ld elements) as a 2-D map, box = {64, box_rows}.
+int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FIDM_REQUIRE(r == CUDA_SUCCESS, FIDM_E_DRIVER, "cuTensorMapEncodeTiled(matrix cols=%d rows=%d ld=%d box=%d) failed: %d",
+               cols, rows, ld, box_rows, (int)r);
+  return 0;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_div(int v, int cap) { int p = 1; while (p * 2 <= cap && v % (p * 2) == 0) p *= 2; return p; }
+
+// Pixel box of an M tile: TW * TH * TN == 128, TW | W, TH | H.
+int pick_pixel_box(int W, int H, int* tw, int* th, int* tn) {
+  const int w = pow2_div(W, 128);
+  const int h = pow2_div(H, 128 / w);
+  *tw = w; *th = h; *tn = 128 / (w * h);
+  (void)pow2_floor;
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  ConvTcParams p;
+  p.B = a.batch; p.H = a.height; p.W = a.width;
+  pick_pixel_box(a.width, a.height, &p.TW, &p.TH, &p.TN);
+  FIDM_REQUIRE(p.TN <= 256, FIDM_E_SHAPE, "conv_tc: image %dx%d too small for a 128-pixel tile", a.height, a.width);
+  p.tiles_w = a.width / p.TW; p.tiles_h = a.height / p.TH; p.tiles_n = (a.batch + p.TN - 1) / p.TN;
+  p.n_blocks = a.cout / BLOCK_N;
+  p.ksize = a.ksize; p.kc1 = a.cin / 64; p.cin1 = a.cin;
+  p.kc2 = a.x2 ? a.cin2 / 64 : 0;
+  p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
+  p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr;
+  p.cout_valid = a.cout_valid;
+
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
+  int rc;
+  if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, BLOCK_N))) return rc;
+  if (a.x2) {
+    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N))) return rc;
+  } else {
+    tmA2 = tmA; tmB2 = tmB;
+  }
+  if (!a.y_nchw_f32) {
+    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, p.TW, p.TH, p.TN))) return rc;
+  } else {
+    tmY = tmA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  const int grid = total < num_sms() ? total : num_sms();
+  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmA2, tmB2, tmY, p);
+  FIDM_CHECK_LAUNCH("conv_tc");
+  return 0;
+}
+
+}  // namespace fidm
+
+extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(a && a->x && a->w && a->y, FIDM_E_BADARG, "conv_tc: null x/w/y");
+  FIDM_REQUIRE(a->dtype == FIDM_BF16, FIDM_E_BADARG, "conv_tc: dtype must be bf16");
+  FIDM_REQUIRE(a->stride == 1 && (a->ksize == 1 || a->ksize == 3), FIDM_E_SHAPE, "conv_tc: only stride 1, ksize 1|3");
+  FIDM_REQUIRE(a->cin % 64 == 0 && a->cin > 0, FIDM_E_SHAPE, "conv_tc: cin %d must be a multiple of 64", a->cin);
+  FIDM_REQUIRE(a->cout % 16 == 0, FIDM_E_SHAPE, "conv_tc: cout %d must be a multiple of 16", a->cout);
+  if (a->x2) FIDM_REQUIRE(a->w2 && a->cin2 % 64 == 0 && a->cin2 > 0, FIDM_E_SHAPE, "conv_tc: bad second source");
+  FIDM_REQUIRE(a->cout_valid > 0 && a->cout_valid <= a->cout, FIDM_E_BADARG, "conv_tc: cout_valid");
+  if (a->bias) FIDM_REQUIRE((uintptr_t)a->bias % 16 == 0, FIDM_E_ALIGN, "conv_tc: bias must be 16-byte aligned");
+  if (a->row_add)
+    FIDM_REQUIRE((uintptr_t)a->row_add % 16 == 0 && a->ld_row_add % 4 == 0, FIDM_E_ALIGN, "conv_tc: row_add alignment");
+  if (a->residual)
+    FIDM_REQUIRE((uintptr_t)a->residual % 16 == 0 && a->ld_res % 8 == 0, FIDM_E_ALIGN, "conv_tc: residual alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->cout % 64 != 0 || a->y_nchw_f32) {
+    FIDM_REQUIRE(a->y_nchw_f32 && a->cout == 16 && !a->residual, FIDM_E_SHAPE,
+                 "conv_tc: cout %d is only supported as the 16-wide fp32-NCHW head", a->cout);
+    return launch_conv_tc<16>(*a, st);
+  }
+  // Widest N tile that still yields about one tile per SM; narrow tiles for the small low-resolution layers.
+  int tw, th, tn;
+  pick_pixel_box(a->width, a->height, &tw, &th, &tn);
+  const long long m_tiles = (long long)(a->width / tw) * (a->height / th) * ((a->batch + tn - 1) / tn);
+  const int want = (num_sms() * 3) / 4;
+  if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want) return launch_conv_tc<256>(*a, st);
+  if (a->cout % 128 == 0 && m_tiles * (a->cout / 128) >= want) return launch_conv_tc<128>(*a, st);
+  return launch_conv_tc<64>(*a, st);
+}

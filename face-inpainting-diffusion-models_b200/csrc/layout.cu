@@ -1,0 +1,115 @@
+// Layout converters between the reference's fp32 NCHW tensors and the NHWC (bf16|fp32) activations
+// used inside the UNet, plus the one-time OIHW -> KRSC weight repack.
+#include "common.cuh"
+
+namespace fidm {
+
+struct PackParams { fidm_pack_args a; };
+
+// One thread per pixel: reads are coalesced across the warp (consecutive pixels of one channel
+// plane), writes are one contiguous c_pad-wide run per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
+  const fidm_pack_args& a = p.a;
+  const long long total = (long long)a.batch * a.hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.hw);
+    const int px = (int)(i % a.hw);
+    T* dst = reinterpret_cast<T*>(a.dst) + i * a.ld_dst;
+    int c = 0;
+    for (int s = 0; s < a.n_src; ++s) {
+      const float* src = a.src[s] + (long long)b * a.src_channels[s] * a.hw + px;
+      for (int r = 0; r < a.src_repeat[s]; ++r)
+        for (int k = 0; k < a.src_channels[s]; ++k) dst[c++] = from_f32<T>(src[(long long)k * a.hw]);
+    }
+    for (; c < a.c_pad; ++c) dst[c] = from_f32<T>(0.0f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_kernel(const T* __restrict__ src, int ld, float* __restrict__ dst,
+                                                      int batch, int hw, int channels) {
+  const long long total = (long long)batch * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int px = (int)(i % hw);
+    const T* s = src + i * ld;
+    for (int c = 0; c < channels; ++c) dst[((long long)b * channels + c) * hw + px] = to_f32<T>(s[c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ w, T* __restrict__ dst, int cout,
+                                                      int cin, int ks, int cout_pad, int cin_pad) {
+  const long long total = (long long)cout_pad * ks * ks * cin_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int tap = (int)((i / cin_pad) % (ks * ks));
+    const int co = (int)(i / ((long long)cin_pad * ks * ks));
+    float v = 0.0f;
+    if (co < cout && ci < cin) v = w[((long long)co * cin + ci) * ks * ks + tap];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+static unsigned grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace fidm
+
+extern "C" int fidm_pack_nchw_to_nhwc(const fidm_pack_args* a, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(a && a->dst, FIDM_E_BADARG, "pack: null args");
+  FIDM_REQUIRE(a->n_src >= 1 && a->n_src <= 4, FIDM_E_BADARG, "pack: n_src %d", a->n_src);
+  int c = 0;
+  for (int s = 0; s < a->n_src; ++s) {
+    FIDM_REQUIRE(a->src[s] && a->src_channels[s] > 0 && a->src_repeat[s] > 0, FIDM_E_BADARG, "pack: bad source %d", s);
+    c += a->src_channels[s] * a->src_repeat[s];
+  }
+  FIDM_REQUIRE(c <= a->c_pad && a->c_pad <= a->ld_dst, FIDM_E_SHAPE, "pack: %d channels > c_pad %d (ld %d)", c,
+               a->c_pad, a->ld_dst);
+  PackParams p;
+  p.a = *a;
+  const unsigned g = grid_for((long long)a->batch * a->hw);
+  if (a->dst_dtype == FIDM_BF16)
+    pack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    pack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+  FIDM_CHECK_LAUNCH("pack_nchw_to_nhwc");
+  return 0;
+}
+
+extern "C" int fidm_unpack_nhwc_to_nchw(const void* src, int32_t src_dtype, int32_t ld_src, float* dst, int32_t batch,
+                                        int32_t hw, int32_t channels, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(src && dst && channels <= ld_src, FIDM_E_BADARG, "unpack: bad args");
+  const unsigned g = grid_for((long long)batch * hw);
+  if (src_dtype == FIDM_BF16)
+    unpack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, dst, batch, hw, channels);
+  else
+    unpack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, dst, batch, hw, channels);
+  FIDM_CHECK_LAUNCH("unpack_nhwc_to_nchw");
+  return 0;
+}
+
+extern "C" int fidm_repack_weight_oihw_to_krsc(const float* w, void* dst, int32_t dst_dtype, int32_t cout, int32_t cin,
+                                               int32_t ksize, int32_t cout_pad, int32_t cin_pad, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(w && dst && cout_pad >= cout && cin_pad >= cin && (ksize == 1 || ksize == 3), FIDM_E_BADARG,
+               "repack: bad args");
+  const unsigned g = grid_for((long long)cout_pad * ksize * ksize * cin_pad);
+  if (dst_dtype == FIDM_BF16)
+    repack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, cout, cin, ksize, cout_pad, cin_pad);
+  else
+    repack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(w, (float*)dst, cout, cin, ksize, cout_pad, cin_pad);
+  FIDM_CHECK_LAUNCH("repack_weight");
+  return 0;
+}

@@ -1,0 +1,428 @@
+"""Execution plan of one UNet evaluation on a B200.
+
+The reference evaluates the UNet as ~700 eager ATen launches on NCHW fp32 tensors
+(`unet.py:154-173`).  Here the topology (`arch.py`) is compiled once per (batch, H, W) into a flat
+list of C-ABI kernel calls on NHWC activations:
+
+  * weights are repacked once: OIHW fp32 -> KRSC bf16 (stem Cin 9 -> 64, head Cout 6 -> 16);
+  * `torch.cat([h, hs.pop()], 1)` (`unet.py:170`) never runs: every producer of `h` / `hs[i]` writes
+    straight into its channel slice of a pre-planned concat buffer (pixel stride `ld`);
+  * GroupNorm+SiLU(+scale/shift)(+2x resample) is one K2 call, conv+bias+emb+residual(+1x1 skip)
+    one K1 call, attention one K3 call, the whole timestep path three K5 calls;
+  * the list is captured into a CUDA graph after one eager warm-up, so an evaluation is a single
+    graph launch (no Python, no per-kernel launch latency).
+
+precision "bf16": tcgen05 tensor-core kernels, bf16 storage, fp32 accumulate / statistics / softmax.
+precision "fp32": FFMA verification mode (north star: eps within rel-L2 1e-5 of the reference).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from .arch import Topology
+
+
+class Ref:
+    """A [B,H,W,channels] NHWC view: channel slice [c0, c0+channels) of `storage` [B,H,W,ld]."""
+
+    __slots__ = ("storage", "c0", "channels", "H", "W")
+
+    def __init__(self, storage, c0, channels, H, W):
+        self.storage, self.c0, self.channels, self.H, self.W = storage, c0, channels, H, W
+
+    @property
+    def ld(self):
+        return self.storage.shape[-1]
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.storage.data_ptr() + self.c0 * self.storage.element_size())
+
+
+class _Pool:
+    """Plan-time scratch allocator: buffers live as long as the plan, and are recycled between
+    layers because execution is strictly sequential on one stream."""
+
+    def __init__(self, device, dtype):
+        self.device, self.dtype = device, dtype
+        self.free = {}
+        self.all = []
+
+    def get(self, B, H, W, Cn):
+        key = (B, H, W, Cn)
+        lst = self.free.setdefault(key, [])
+        if lst:
+            return lst.pop()
+        t = torch.empty(B, H, W, Cn, device=self.device, dtype=self.dtype)
+        self.all.append(t)
+        return t
+
+    def put(self, t):
+        self.free.setdefault(tuple(t.shape), []).append(t)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.all)
+
+
+STEM_CIN_PAD = 64
+HEAD_COUT_PAD = 16
+
+
+class Weights:
+    """Device-resident, kernel-ready parameters (built once per model / device / precision)."""
+
+    def __init__(self, topo: Topology, sd, device, precision):
+        self.topo, self.device, self.precision = topo, device, precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.code = L.dtype_code(self.dtype)
+        self.conv = {}      # name -> (krsc weight, bias fp32, cin_pad, cout_pad, ksize)
+        self.vec = {}       # name -> fp32 vector (GroupNorm gamma/beta)
+        lib = L.lib()
+
+        def f32(name):
+            return sd[name].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        def conv(name, cin_pad=None, cout_pad=None, extra_bias=None):
+            w = f32(name + ".weight")
+            if w.dim() == 3:                      # Conv1d k=1 (nn.py:252,254)
+                w = w.unsqueeze(-1)
+            cout, cin, ks, _ = w.shape
+            cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+            dst = torch.empty(cout_pad, ks, ks, cin_pad, device=device, dtype=self.dtype)
+            L.check(lib.fidm_repack_weight_oihw_to_krsc(L.ptr(w), L.ptr(dst), self.code, cout, cin, ks,
+                                                        cout_pad, cin_pad, L.stream()), "repack " + name)
+            b = torch.zeros(cout_pad, device=device, dtype=torch.float32)
+            b[:cout] = f32(name + ".bias")
+            if extra_bias is not None:
+                b[:cout] += extra_bias
+            self.conv[name] = (dst, b, cin_pad, cout_pad, ks)
+
+        def norm(name):
+            self.vec[name + ".weight"] = f32(name + ".weight")
+            self.vec[name + ".bias"] = f32(name + ".bias")
+
+        emb_w, emb_b, self.emb_off = [], [], {}
+        off = 0
+        from .arch import all_layers
+        for layer in all_layers(topo):
+            n = layer.name
+            if layer.kind == "stem":
+                conv(n, cin_pad=STEM_CIN_PAD)
+            elif layer.kind == "res":
+                norm(n + ".in_layers.0")
+                conv(n + ".in_layers.2")
+                norm(n + ".out_layers.0")
+                if layer.skip == "identity":
+                    conv(n + ".out_layers.3")
+                else:
+                    conv(n + ".skip_connection")
+                    conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"))
+                w = f32(n + ".emb_layers.1.weight")
+                emb_w.append(w)
+                emb_b.append(f32(n + ".emb_layers.1.bias"))
+                self.emb_off[n] = off
+                off += w.shape[0]
+            elif layer.kind == "attn":
+                norm(n + ".norm")
+                conv(n + ".qkv")
+                conv(n + ".proj_out")
+            elif layer.kind == "down" and layer.use_conv:
+                conv(n + ".op")
+            elif layer.kind == "up" and layer.use_conv:
+                conv(n + ".conv")
+        norm("out.0")
+        conv("out.2", cout_pad=HEAD_COUT_PAD)
+        self.emb_total = off
+        self.emb_w = torch.cat(emb_w, 0).contiguous()
+        self.emb_b = torch.cat(emb_b, 0).contiguous()
+        self.te0_w, self.te0_b = f32("time_embed.0.weight"), f32("time_embed.0.bias")
+        self.te2_w, self.te2_b = f32("time_embed.2.weight"), f32("time_embed.2.bias")
+        mc = topo.cfg["model_channels"]
+        half = mc // 2
+        # computed on the CPU exactly as the reference does (nn.py:54-56), then uploaded
+        self.freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half
+                               ).to(device)
+        torch.cuda.synchronize(device)
+
+
+class Plan:
+    """Flat kernel schedule + buffers for one (batch, H, W)."""
+
+    def __init__(self, weights: Weights, B, H, W, use_graph=True):
+        self.w, self.B, self.H, self.W = weights, B, H, W
+        topo = weights.topo
+        dev, dt = weights.device, weights.dtype
+        self.ops = []
+        self.pool = _Pool(dev, dt)
+        self.keep = []
+        cfg = topo.cfg
+        mc, ted = cfg["model_channels"], topo.time_embed_dim
+        self.ssn = cfg["use_scale_shift_norm"]
+        lib = L.lib()
+        self.lib = lib
+
+        # ---- static inputs / outputs
+        self.x_in = torch.zeros(B, H, W, STEM_CIN_PAD, device=dev, dtype=dt)
+        self.t_in = torch.zeros(B, device=dev, dtype=torch.float32)
+        self.out = torch.empty(B, topo.out_channels, H, W, device=dev, dtype=torch.float32)
+        self.stats = torch.zeros(B * 32 * 2, device=dev, dtype=torch.float64)
+
+        # ---- K5: timestep path
+        self.temb = torch.empty(B, mc, device=dev, dtype=torch.float32)
+        self.e1 = torch.empty(B, ted, device=dev, dtype=torch.float32)
+        self.emb = torch.empty(B, ted, device=dev, dtype=torch.float32)
+        self.emb_all = torch.empty(B, weights.emb_total, device=dev, dtype=torch.float32)
+        w = weights
+        self._op(lib.fidm_timestep_embedding, L.ptr(self.t_in), L.ptr(w.freqs), L.ptr(self.temb), B, mc)
+        self._op(lib.fidm_linear_small, L.ptr(self.temb), L.ptr(w.te0_w), L.F32, L.ptr(w.te0_b), L.ptr(self.e1),
+                 B, mc, ted, 0)
+        self._op(lib.fidm_linear_small, L.ptr(self.e1), L.ptr(w.te2_w), L.F32, L.ptr(w.te2_b), L.ptr(self.emb),
+                 B, ted, ted, 1)
+        self._op(lib.fidm_linear_small, L.ptr(self.emb), L.ptr(w.emb_w), L.F32, L.ptr(w.emb_b), L.ptr(self.emb_all),
+                 B, ted, w.emb_total, 1)
+
+        # ---- concat buffers of the output path (unet.py:170): cat_j = [h | hs.pop()]
+        n_in = len(topo.input_blocks)
+        assert n_in == len(topo.output_blocks)
+        res = [(H // b.ds, W // b.ds) for b in topo.input_blocks]
+        self.cats = []
+        for j, blk in enumerate(topo.output_blocks):
+            i = n_in - 1 - j
+            hh, ww = res[i]
+            self.cats.append(torch.empty(B, hh, ww, blk.cin, device=dev, dtype=dt))
+
+        def in_dst(i):
+            j = n_in - 1 - i
+            blk = topo.output_blocks[j]
+            hh, ww = res[i]
+            return Ref(self.cats[j], blk.cin - blk.skip_ch, blk.skip_ch, hh, ww)
+
+        def h_dst(j):
+            blk = topo.output_blocks[j]
+            hh, ww = res[n_in - 1 - j]
+            return Ref(self.cats[j], 0, blk.cin - blk.skip_ch, hh, ww)
+
+        # ---- walk the topology
+        x = Ref(self.x_in, 0, STEM_CIN_PAD, H, W)
+        for i, blk in enumerate(topo.input_blocks):
+            x = self._block(blk, x, in_dst(i))
+        x = self._block(topo.middle, x, h_dst(0))
+        for j, blk in enumerate(topo.output_blocks):
+            full = Ref(self.cats[j], 0, blk.cin, x.H, x.W)
+            if j + 1 < len(topo.output_blocks):
+                dst = h_dst(j + 1)
+            else:
+                dst = self._new(self.H, self.W, blk.cout)
+            x = self._block(blk, full, dst)
+        # ---- head: out = conv3x3(SiLU(GN(h)))  (unet.py:148-152,173)
+        a = self._new(x.H, x.W, x.channels)
+        self._gn(x, a, "out.0", silu=True)
+        self._conv("out.2", a, None, nchw_out=self.out, cout_valid=topo.out_channels)
+
+        self.graph = None
+        self.use_graph = use_graph
+        self._warm = False
+
+    # ------------------------------------------------------------------ op builders
+    def _op(self, fn, *args):
+        self.ops.append((fn, args))
+
+    def _new(self, H, W, Cn):
+        return Ref(self.pool.get(self.B, H, W, Cn), 0, Cn, H, W)
+
+    def _release(self, ref):
+        self.pool.put(ref.storage)
+
+    def _gn(self, x, y, name, silu, scale_shift=None, resample=L.RESAMPLE_NONE, y_raw=None, skip_norm=False):
+        w = self.w
+        a = L.GnArgs()
+        a.dtype, a.batch, a.height, a.width, a.channels, a.groups = w.code, self.B, x.H, x.W, x.channels, 32
+        a.eps = 1e-5
+        a.x, a.ld_x = x.ptr, x.ld
+        if not skip_norm:
+            a.gamma, a.beta = L.ptr(w.vec[name + ".weight"]), L.ptr(w.vec[name + ".bias"])
+        if scale_shift is not None:
+            off = scale_shift
+            a.scale_shift = L.ptr(self.emb_all, off * 4)
+            a.ld_ss = self.emb_all.shape[1]
+        a.silu, a.resample, a.skip_norm = int(silu), resample, int(skip_norm)
+        a.y, a.ld_y = y.ptr, y.ld
+        if y_raw is not None:
+            a.y_raw, a.ld_raw = y_raw.ptr, y_raw.ld
+        a.stats = L.ptr(self.stats)
+        self.keep.append(a)
+        self._op(self.lib.fidm_groupnorm_silu_nhwc, C.byref(a))
+
+    def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
+              cout_valid=None):
+        w = self.w
+        wt, bias, cin_pad, cout_pad, ks = w.conv[name]
+        assert x.channels == cin_pad, (name, x.channels, cin_pad)
+        a = L.ConvArgs()
+        a.dtype, a.batch, a.height, a.width = w.code, self.B, x.H, x.W
+        a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
+        a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
+        if x2 is not None:
+            w2 = w.conv[name2][0]
+            a.x2, a.ld_x2, a.cin2, a.w2 = x2.ptr, x2.ld, x2.channels, L.ptr(w2)
+        a.bias = L.ptr(bias)
+        if row_add is not None:
+            a.row_add = L.ptr(self.emb_all, row_add * 4)
+            a.ld_row_add = self.emb_all.shape[1]
+        if residual is not None:
+            a.residual, a.ld_res = residual.ptr, residual.ld
+        if nchw_out is not None:
+            a.y, a.ld_y, a.y_nchw_f32 = L.ptr(nchw_out), 0, 1
+        else:
+            a.y, a.ld_y = y.ptr, y.ld
+        a.cout_valid = cout_valid or cout_pad
+        self.keep.append(a)
+        tc_ok = (w.precision == "bf16" and stride == 1 and cin_pad % 64 == 0 and
+                 (cout_pad % 64 == 0 or (nchw_out is not None and cout_pad == 16 and residual is None)) and
+                 (x2 is None or x2.channels % 64 == 0))
+        fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
+        self._op(fn, C.byref(a))
+
+    def _attention(self, qkv, out, heads, head_dim):
+        w = self.w
+        a = L.AttnArgs()
+        a.dtype, a.batch, a.tokens, a.heads, a.head_dim = w.code, self.B, qkv.H * qkv.W, heads, head_dim
+        a.qkv, a.ld_qkv, a.out, a.ld_out = qkv.ptr, qkv.ld, out.ptr, out.ld
+        self.keep.append(a)
+        tc_ok = (w.precision == "bf16" and head_dim == 64 and a.tokens % 64 == 0 and
+                 hasattr(self.lib, "fidm_attention_qkv_nhwc_bf16") and Plan.TC_ATTENTION)
+        fn = self.lib.fidm_attention_qkv_nhwc_bf16 if tc_ok else self.lib.fidm_attention_qkv_nhwc_simt
+        self._op(fn, C.byref(a))
+
+    TC_ATTENTION = True
+
+    # ------------------------------------------------------------------ layers
+    def _block(self, blk, x, dst):
+        layers = blk.layers
+        for k, layer in enumerate(layers):
+            last = k == len(layers) - 1
+            if layer.kind == "stem":
+                y = dst
+                self._conv(layer.name, x, y)
+            elif layer.kind == "res":
+                y = self._res(layer, x, dst if last else None)
+            elif layer.kind == "attn":
+                y = self._attn(layer, x, dst if last else None)
+            elif layer.kind == "down":
+                y = self._down(layer, x, dst if last else None)
+            elif layer.kind == "up":
+                y = self._up(layer, x, dst if last else None)
+            else:
+                raise NotImplementedError(layer.kind)
+            if k > 0:
+                self._release(x)          # intermediate of this block
+            x = y
+        return x
+
+    def _res(self, layer, x, dst):
+        """ResBlock._forward (nn.py:189-212)."""
+        n, w = layer.name, self.w
+        H, W = x.H, x.W
+        if layer.up:
+            H, W, mode = 2 * H, 2 * W, L.RESAMPLE_UP
+        elif layer.down:
+            H, W, mode = H // 2, W // 2, L.RESAMPLE_DOWN
+        else:
+            mode = L.RESAMPLE_NONE
+        a1 = self._new(H, W, layer.cin)
+        xr = self._new(H, W, layer.cin) if mode != L.RESAMPLE_NONE else None
+        self._gn(x, a1, n + ".in_layers.0", silu=True, resample=mode, y_raw=xr)
+        h = self._new(H, W, layer.cout)
+        off = w.emb_off[n]
+        self._conv(n + ".in_layers.2", a1, h, row_add=None if self.ssn else off)
+        self._release(a1)
+        a2 = self._new(H, W, layer.cout)
+        self._gn(h, a2, n + ".out_layers.0", silu=True, scale_shift=off if self.ssn else None)
+        self._release(h)
+        y = dst if dst is not None else self._new(H, W, layer.cout)
+        xs = xr if xr is not None else x
+        if layer.skip == "identity":
+            self._conv(n + ".out_layers.3", a2, y, residual=xs)
+        else:
+            self._conv(n + ".out_layers.3", a2, y, x2=xs, name2=n + ".skip_connection")
+        self._release(a2)
+        if xr is not None:
+            self._release(xr)
+        return y
+
+    def _attn(self, layer, x, dst):
+        """AttentionBlock._forward (nn.py:259-265)."""
+        n, Cn = layer.name, layer.channels
+        a = self._new(x.H, x.W, Cn)
+        self._gn(x, a, n + ".norm", silu=False)
+        qkv = self._new(x.H, x.W, 3 * Cn)
+        self._conv(n + ".qkv", a, qkv)
+        self._release(a)
+        o = self._new(x.H, x.W, Cn)
+        self._attention(qkv, o, layer.heads, Cn // layer.heads)
+        self._release(qkv)
+        y = dst if dst is not None else self._new(x.H, x.W, Cn)
+        self._conv(n + ".proj_out", o, y, residual=x)
+        self._release(o)
+        return y
+
+    def _down(self, layer, x, dst):
+        """Downsample (nn.py:115-133): conv3x3 stride 2, or 2x average pooling."""
+        H, W = x.H // 2, x.W // 2
+        y = dst if dst is not None else self._new(H, W, layer.channels)
+        if layer.use_conv:
+            self._conv(layer.name + ".op", x, y, stride=2)
+        else:
+            self._gn(x, y, None, silu=False, resample=L.RESAMPLE_DOWN, skip_norm=True)
+        return y
+
+    def _up(self, layer, x, dst):
+        """Upsample (nn.py:92-112): nearest 2x, then optional conv3x3."""
+        H, W = 2 * x.H, 2 * x.W
+        if layer.use_conv:
+            u = self._new(H, W, layer.channels)
+            self._gn(x, u, None, silu=False, resample=L.RESAMPLE_UP, skip_norm=True)
+            y = dst if dst is not None else self._new(H, W, layer.channels)
+            self._conv(layer.name + ".conv", u, y)
+            self._release(u)
+        else:
+            y = dst if dst is not None else self._new(H, W, layer.channels)
+            self._gn(x, y, None, silu=False, resample=L.RESAMPLE_UP, skip_norm=True)
+        return y
+
+    # ------------------------------------------------------------------ execution
+    def launch_all(self):
+        st = L.stream()
+        for fn, args in self.ops:
+            rc = fn(*args, st)
+            if rc != 0:
+                L.check(rc, fn.__name__)
+
+    def run(self):
+        """Evaluate the UNet on self.x_in / self.t_in into self.out."""
+        if not self.use_graph:
+            self.launch_all()
+            return self.out
+        if self.graph is None:
+            if not self._warm:
+                self.launch_all()                     # sets func attributes, resolves driver entry points
+                torch.cuda.current_stream().synchronize()
+                self._warm = True
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.launch_all()
+            self.graph = g
+        self.graph.replay()
+        return self.out
+
+    def n_launches(self):
+        """Kernel launches per evaluation (groupnorm = stats + apply; memset nodes not counted)."""
+        n = 0
+        for fn, args in self.ops:
+            if fn is self.lib.fidm_groupnorm_silu_nhwc:
+                n += 1 if args[0]._obj.skip_norm else 2
+            else:
+                n += 1
+        return n

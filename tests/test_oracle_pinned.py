@@ -1,0 +1,102 @@
+"""CPU: the oracle restatement (oracle/*.py) against the golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  This is what pins the oracle; the reference has no tests."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import fidm_b200  # noqa: F401
+from fidm_b200.arch import CONFIGS, param_shapes, unet_topology
+from fidm_b200.utils.schedules import get_named_beta_schedule
+from fidm_b200.utils.synth import synth_batch, synth_state_dict
+from oracle import diffusion_oracle as dor
+from oracle import unet_oracle as uor
+
+from helpers import psnr, seeded_noise
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "state_dict_layout.json")))
+    for name, cfg in CONFIGS.items():
+        mine = [["base_model." + k, list(s)] for k, s in param_shapes(unet_topology(**cfg))]
+        assert mine == ref[name], name
+
+
+def test_schedule_tables_match_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "schedules.json")))
+    for key, vals in ref.items():
+        sched, T = key.rsplit("_", 1)
+        T = int(T)
+        with np.errstate(divide="ignore"):
+            tab = dor.Tables(get_named_beta_schedule(sched, T))
+        idx = [0, 1, T // 2, T - 1]
+        for k, v in vals.items():
+            got = [float(getattr(tab, k)[i]) for i in idx]
+            assert got == v, (key, k)          # float64, exact
+
+
+def test_oracle_sampler_steps_bit_exact(golden_dir):
+    cases = torch.load(os.path.join(golden_dir, "sampler_steps.pt"))
+    assert len(cases) == 108
+    for c in cases:
+        tab = dor.Tables(get_named_beta_schedule(c["sched"], c["T"]))
+        g = torch.Generator().manual_seed(c["seed"])
+        B, C, H, W = c["sample"].shape
+        t, T = c["t"], c["T"]
+        x = torch.randn(B, C, H, W, generator=g) * (1.0 + t / T)
+        gt = torch.rand(B, C, H, W, generator=g) * 2 - 1
+        keep = (torch.rand(B, 1, H, W, generator=g) > 0.4).float()
+        mo = torch.randn(B, 2 * C if c["var_type"] == "learned_range" else C, H, W, generator=g)
+        n_inj = torch.randn(B, C, H, W, generator=g)
+        z = torch.randn(B, C, H, W, generator=g)
+        xi = dor.inject(tab, x, t, gt, keep, n_inj, c["cumulative"])
+        assert torch.equal(xi, c["x_inj"])
+        if c["mode"] == "ddim":
+            s, x0 = dor.ddim_update(tab, mo, xi, t, z, c["eta"], c["var_type"])
+        else:
+            s, x0 = dor.ddpm_update(tab, mo, xi, t, z, c["var_type"])
+        assert torch.equal(s, c["sample"]) and torch.equal(x0, c["pred_xstart"])
+        # known-region pixels are exactly the noised ground truth
+        m = keep.expand_as(xi) == 1
+        wg = dor.inject(tab, torch.zeros_like(x), t, gt, torch.ones_like(keep), n_inj, c["cumulative"])
+        assert torch.equal(xi[m], wg[m])
+
+
+def test_oracle_unet_forward_matches_reference(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "t64_forward.pt"))
+    cfg = CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=gold["seed_weights"])
+    data = synth_batch(2, 64, seed=gold["seed_data"])
+    with torch.no_grad():
+        out = uor.inpaint_forward(sd, cfg, gold["x"], gold["t"], data["masked_image"], data["mask"])
+    assert torch.allclose(out, gold["out"], rtol=1e-4, atol=1e-5)
+    assert ((out - gold["out"]).norm() / gold["out"].norm()).item() < 1e-5
+
+
+def test_oracle_unet_variants_match_reference(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "t32_variants.pt"))
+    for tag, g in gold.items():
+        sd = synth_state_dict(g["cfg"], seed=g["seed_weights"])
+        data = synth_batch(2, 32, seed=g["seed_data"])
+        with torch.no_grad():
+            out = uor.inpaint_forward(sd, g["cfg"], g["x"], g["t"], data["masked_image"], data["mask"])
+        assert ((out - g["out"]).norm() / g["out"].norm()).item() < 1e-5, tag
+
+
+def test_oracle_ddim50_loop_matches_reference(golden_dir):
+    """BASELINE config #1: T64, DDIM-50 cosine, B=1, injection on -- the full loop on the CPU."""
+    gold = torch.load(os.path.join(golden_dir, "t64_ddim50.pt"))
+    cfg = CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=gold["seed_weights"])
+    data = synth_batch(1, 64, seed=gold["seed_data"])
+    gt, keep = data["gt"], data["gt_keep_mask"]
+    tab = dor.Tables(get_named_beta_schedule("cosine", gold["T"]))
+    seed, shape = gold["seed_noise"], (1, 3, 64, 64)
+    trace = []
+    with torch.no_grad():
+        out = dor.sample_loop(tab, lambda x, t, **k: uor.inpaint_forward(sd, cfg, x, t, gt * keep, 1 - keep),
+                              shape, ddim=True, x_T=seeded_noise("xT", 0, shape, seed), gt=gt, keep=keep,
+                              noise_fn=lambda kind, t: seeded_noise(kind, t, shape, seed), trace=trace)
+    assert psnr(out, gold["final"]) > 60
+    assert psnr(trace[24]["pred_xstart"], gold["pred_xstart_t25"]) > 60
