@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the masked-inpainting sampling path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload adm256|ref_ffhq256|t64]
+
+A "step" is one complete pass of the hot path over one batch: a full `ddim_sample_loop` (DDIM-100,
+cosine schedule, known-region injection on) for `--batch` 256x256 images per GPU on the ADM256
+9-channel UNet (BASELINE configs[1]).  Prints ONE JSON line (rank 0).
+
+`value`  : images/s with gt / masks / weights resident in HBM (CUDA-event time, max over ranks).
+`e2e`    : the same metric through the public API with HOST buffers: pinned gt + mask -> H2D, the loop,
+           D2H of the finished images, all inside the timed region.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv, 256->256 @ 256x256) timed alone with CUDA
+           events: algorithmic FLOPs per launch / average launch time vs the measured bf16 peak.
+`cpu_baseline`: the CPU oracle (a port of the reference; /root/reference does not travel to the GPU
+           box) timed on the host cores on a bounded sample of the same workload.
+`--impl reference`: the reference's CPU implementation of the path (oracle port), all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "adm256": dict(cfg="ADM256", size=256, ddim_steps=100, schedule="cosine", gflop_per_image_eval=2241.48,
+                   label="ADM256 9-ch UNet (Improved-DDPM 256 config, attn 32/16/8), 256x256, DDIM-100 cosine, "
+                         "known-region injection on (BASELINE configs[1])"),
+    "ref_ffhq256": dict(cfg="REF_FFHQ256", size=256, ddim_steps=100, schedule="cosine", gflop_per_image_eval=388.84,
+                        label="REF-FFHQ256 9-ch UNet (train_inpainting.py:208-224), 256x256, DDIM-100 cosine, "
+                              "injection on"),
+    "t64": dict(cfg="T64", size=64, ddim_steps=50, schedule="cosine", gflop_per_image_eval=20.03,
+                label="T64 9-ch UNet, 64x64, DDIM-50 cosine, injection on (BASELINE configs[0])"),
+}
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update(hbm_gbs=m["hbm_gbs"], bf16_tflops=m["bf16_tflops"],
+                 bf16_tflops_sustained=m.get("bf16_tflops_sustained", m["bf16_tflops"]), src="measured")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_sample(wl, evals, threads=None):
+    """Time `evals` oracle UNet evaluations + sampler steps at batch 1 on the host; returns
+    (images/s extrapolated to the full loop, seconds per eval+step, cores)."""
+    import fidm_b200 as F
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    from oracle import diffusion_oracle as dor
+    from oracle import unet_oracle as uor
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = F.CONFIGS[wl["cfg"]]
+    sd = synth_state_dict(cfg, seed=0)
+    data = synth_batch(1, wl["size"], seed=0)
+    gt, keep = data["gt"], data["gt_keep_mask"]
+    tab = dor.Tables(F.get_named_beta_schedule(wl["schedule"], wl["ddim_steps"]))
+    shape = (1, 3, wl["size"], wl["size"])
+    x = torch.randn(*shape)
+    times = []
+    with torch.no_grad():
+        for i in range(evals):
+            t = wl["ddim_steps"] - 1 - i
+            t0 = time.perf_counter()
+            x = dor.inject(tab, x, t, gt, keep, torch.randn_like(gt))
+            out = uor.inpaint_forward(sd, cfg, x, torch.full((1,), t), gt * keep, 1 - keep)
+            x, _ = dor.ddim_update(tab, out, x, t, torch.randn_like(x))
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
+    reference cannot travel to the GPU box), each step = one UNet eval + sampler step at batch 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.warmup + args.steps
+    times, cores = cpu_oracle_sample(wl, n)
+    t = times[args.warmup:]
+    sec = sum(t) / len(t)
+    value = 1.0 / (sec * wl["ddim_steps"])
+    sample = f"{len(t)} x (UNet eval + injection + DDIM update) at batch 1, extrapolated x{wl['ddim_steps']} steps"
+    line = {"impl": "reference", "metric": "inpainted 256x256 images/s (DDIM-100)" if wl["size"] == 256 else
+            "inpainted images/s", "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "per_gpu_batch": 1},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="adm256", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU")
+    ap.add_argument("--ddim-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-only", action="store_true", help="only time UNet evaluations (ms per eval)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.ddim_steps:
+        wl["ddim_steps"] = args.ddim_steps
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import fidm_b200 as F
+    from fidm_b200 import ops
+    from fidm_b200.parallel import gather_batch
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F._lib.check(F._lib.lib().fidm_device_supported(local), "device")
+
+    cfg = F.CONFIGS[wl["cfg"]]
+    B, S, T = args.batch, wl["size"], wl["ddim_steps"]
+    model = F.DiffusionInpaintingModel(F.UNetModel(**dict(cfg, in_channels=3)))
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    model.to(dev)
+    model.base_model.set_precision(args.precision)
+    fn = F.InpaintingModelFn(model)
+    diffusion = F.create_gaussian_diffusion(steps=T, learn_sigma=True, noise_schedule=wl["schedule"])
+    data = synth_batch(B, S, seed=100 + rank, device=dev)
+    gt, keep = data["gt"], data["gt_keep_mask"]
+    host_gt, host_keep = data["gt"].cpu().pin_memory(), data["gt_keep_mask"].cpu().pin_memory()
+    host_out = torch.empty(B * world if False else B, 3, S, S).pin_memory()
+    torch.manual_seed(1234 + rank)
+    torch.cuda.manual_seed(1234 + rank)
+
+    def loop(g, k):
+        return diffusion.ddim_sample_loop(fn, (B, 3, S, S), model_kwargs={"gt": g, "gt_keep_mask": k}, device=dev,
+                                          eta=0.0, use_inpainting_injection=True)
+
+    def step_device():
+        out = loop(gt, keep)
+        return gather_batch(out, B * world) if world > 1 else out
+
+    def step_e2e():
+        g = host_gt.to(dev, non_blocking=True)
+        k = host_keep.to(dev, non_blocking=True)
+        out = loop(g, k)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn_step, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn_step()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    if args.eval_only:
+        xin = torch.randn(B, 3, S, S, device=dev)
+        tt = torch.full((B,), T // 2, device=dev)
+        for _ in range(5):
+            fn(xin, tt, gt=gt, gt_keep_mask=keep)
+        with ClockSampler(local) as clk:
+            ms_eval = timed(lambda: fn(xin, tt, gt=gt, gt_keep_mask=keep), 40) / 40
+        print(json.dumps({"ms_per_unet_eval": ms_eval, "batch": B, "tflops": wl["gflop_per_image_eval"] * B / ms_eval,
+                          "norm_dtype": os.environ.get("FIDM_NORM_DTYPE", "fp16"), "clocks": clk.summary()}), flush=True)
+        return
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    with ClockSampler(local) as clk:
+        ms = timed(step_device, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    images = B * world * args.steps
+    value = images / (ms / 1e3)
+    e2e_value = images / (ms_e2e / 1e3)
+
+    plan = model.base_model.plan_for(B, S, S)
+    launches_per_loop = T * (plan.n_launches() + 2) + 1          # + pack + K4 per step, + first injection
+    # UNet-only timing (ms per eval at this batch)
+    xin = torch.randn(B, 3, S, S, device=dev)
+    tt = torch.full((B,), T // 2, device=dev)
+    for _ in range(3):
+        fn(xin, tt, gt=gt, gt_keep_mask=keep)
+    ms_eval = timed(lambda: fn(xin, tt, gt=gt, gt_keep_mask=keep), 10) / 10
+    tf_eval = wl["gflop_per_image_eval"] * B / ms_eval            # GFLOP / ms == TFLOP/s
+
+    pk = peaks()
+    line = {
+        "metric": "inpainted 256x256 images/s (DDIM-100)" if S == 256 else "inpainted images/s",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": wl["label"], "per_gpu_batch": B, "global_batch": B * world, "ddim_steps": T,
+                   "parallelism": f"batch-sharded x{world}, no collective in the loop, one all_gather of the outputs",
+                   "l2": f"no flush: one UNet eval streams {plan.pool.nbytes() / 1e9:.1f}+ GB of activations (>> 126 MB L2)",
+                   "cuda_graph": bool(model.base_model.use_cuda_graph)},
+        "ms_per_unet_eval": ms_eval,
+        "unet_eval": {"batch": B, "tflops": tf_eval, "frac_of_sustained_peak": tf_eval / pk["bf16_tflops_sustained"],
+                      "peak_src": pk["src"]},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host_gt.numel() * 4 + host_keep.numel() * 4,
+                "d2h_bytes_per_step": host_out.numel() * 4},
+        "gpu_launches": launches_per_loop * args.steps,
+        "clocks": clk.summary(),
+    }
+
+    if rank == 0:
+        line["roofline"] = dominant_kernel_roofline(ops, dev, pk, B)
+        if world == 1 and not args.no_cpu_baseline:
+            evals = 2 if S == 256 else 5
+            times, cores = cpu_oracle_sample(wl, evals + 1)
+            sec = sum(times[1:]) / len(times[1:])
+            line["cpu_baseline"] = {"value": 1.0 / (sec * T), "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{evals} x (UNet eval + injection + DDIM update) at batch 1 after 1 warm-up, "
+                                              f"extrapolated x{T} steps ({sec:.2f} s per step)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(ops, dev, pk, B):
+    """conv3x3 256->256 @ 256x256 (31 % of ADM256 FLOPs), timed alone on this stream."""
+    import math
+    Cin = Cout = 256
+    H = W = 256
+    x = torch.randn(B, H, W, Cin, device=dev).bfloat16()           # 268 MB at B=8: larger than L2
+    w = ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9))
+    b = torch.zeros(Cout, device=dev)
+    y = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.conv2d(x, w, b, out=y, impl="tc")
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        ops.conv2d(x, w, b, out=y, impl="tc")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * H * W * Cout * Cin * 9
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "conv_tc_kernel<256> (3x3, 256->256, 256x256, batch %d)" % B, "bound": "tensor",
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "peak_src": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": ms,
+            "flops_per_launch": flops, "traffic": None}
+
+
+if __name__ == "__main__":
+    main()

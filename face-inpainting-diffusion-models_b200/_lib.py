@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfidm_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 COEF_COLS = 20
 STEP_INJECT_ONLY, STEP_UPDATE_ONLY, STEP_UPDATE_INJECT = 0, 1, 2
 SAMPLER_DDPM, SAMPLER_DDIM = 0, 1
@@ -39,7 +39,7 @@ class PackArgs(C.Structure):
 
 
 class GnArgs(C.Structure):
-    _fields_ = [("dtype", i32), ("batch", i32), ("height", i32), ("width", i32), ("channels", i32),
+    _fields_ = [("dtype", i32), ("y_dtype", i32), ("batch", i32), ("height", i32), ("width", i32), ("channels", i32),
                 ("groups", i32), ("eps", C.c_float), ("x", vp), ("ld_x", i32),
                 ("gamma", fp), ("beta", fp), ("scale_shift", fp), ("ld_ss", i32),
                 ("silu", i32), ("resample", i32), ("skip_norm", i32), ("y", vp), ("ld_y", i32),
@@ -73,6 +73,7 @@ SYMBOLS = {
     "fidm_timestep_embedding": (C.c_int, [fp, fp, fp, i32, i32, vp]),
     "fidm_linear_small": (C.c_int, [fp, vp, i32, fp, fp, i32, i32, i32, i32, vp]),
     "fidm_groupnorm_silu_nhwc": (C.c_int, [_P(GnArgs), vp]),
+    "fidm_groupnorm_workspace_bytes": (C.c_int64, [i32, i32]),
     "fidm_conv2d_nhwc_bf16": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_conv2d_nhwc_simt": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_attention_qkv_nhwc_bf16": (C.c_int, [_P(AttnArgs), vp]),
@@ -127,6 +128,8 @@ def dtype_code(dt):
         return BF16
     if dt == torch.float32:
         return F32
+    if dt == torch.float16:
+        return F16
     raise ValueError(f"unsupported dtype {dt}")
 
 

@@ -18,7 +18,8 @@
 namespace fidm {
 using namespace sm100;
 
-int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn);
+int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
+                  int f16);
 
 struct AttnTcParams {
   int B, T, heads, C;      // C = heads * 64
@@ -253,8 +254,8 @@ extern "C" int fidm_attention_qkv_nhwc_bf16(const fidm_attn_args* a, fidm_stream
   CUtensorMap tmQKV, tmO;
   int rc;
   // [B][T][3C] viewed as NHWC with H = 1: box = 64 channels x 128 tokens
-  if ((rc = make_nhwc_map(&tmQKV, a->qkv, 3 * Cn, a->tokens, 1, a->batch, a->ld_qkv, 128, 1, 1))) return rc;
-  if ((rc = make_nhwc_map(&tmO, a->out, Cn, a->tokens, 1, a->batch, a->ld_out, 128, 1, 1))) return rc;
+  if ((rc = make_nhwc_map(&tmQKV, a->qkv, 3 * Cn, a->tokens, 1, a->batch, a->ld_qkv, 128, 1, 1, 0))) return rc;
+  if ((rc = make_nhwc_map(&tmO, a->out, Cn, a->tokens, 1, a->batch, a->ld_out, 128, 1, 1, 0))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     FIDM_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));

@@ -35,6 +35,7 @@ struct ConvTcParams {
   int n_blocks;            // Cout / BLOCK_N
   int ksize, kc1, cin1;    // taps = ksize^2, kc1 = Cin/64
   int kc2;                 // Cin2/64 (0: no second source)
+  int ab_f16;              // primary A/B operands are fp16 (normalized activations), else bf16
   const float* bias;
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
@@ -130,7 +131,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 5) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+      // second-source (raw residual stream) operands are always bf16
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(128, BLOCK_N);
+      const uint32_t idesc_main = p.ab_f16 ? umma_idesc_f16(128, BLOCK_N) : idesc_bf16;
+      const int main_iters = p.ksize * p.ksize * p.kc1;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -143,8 +147,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sa + kABytes);
+          const uint32_t idesc = it < main_iters ? idesc_main : idesc_bf16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle atom
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 elements = 32 B) inside the 128-byte swizzle atom
             umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -311,7 +316,8 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // NHWC bf16 tensor [N][H][W][C] (pixel stride ld elements) as a 4-D map, box = {64, bw, bh, bn}.
-int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn) {
+int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
+                  int f16) {
   EncodeTiledFn enc = get_encode_tiled();
   FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
   FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
@@ -319,7 +325,7 @@ int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FIDM_REQUIRE(r == CUDA_SUCCESS, FIDM_E_DRIVER, "cuTensorMapEncodeTiled(NHWC C=%d W=%d H=%d N=%d ld=%d box=%d,%d,%d) failed: %d",
@@ -328,7 +334,7 @@ int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
 }
 
 // Row-major bf16 matrix [rows][cols] (row stride ld elements) as a 2-D map, box = {64, box_rows}.
-int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows) {
+int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows, int f16) {
   EncodeTiledFn enc = get_encode_tiled();
   FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
   FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
@@ -336,7 +342,7 @@ int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FIDM_REQUIRE(r == CUDA_SUCCESS, FIDM_E_DRIVER, "cuTensorMapEncodeTiled(matrix cols=%d rows=%d ld=%d box=%d) failed: %d",
@@ -367,6 +373,8 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
   p.n_blocks = a.cout / BLOCK_N;
   p.ksize = a.ksize; p.kc1 = a.cin / 64; p.cin1 = a.cin;
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
+  p.ab_f16 = a.dtype == FIDM_F16;
+  const int f16 = p.ab_f16;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr;
@@ -374,16 +382,16 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
   int rc;
-  if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN))) return rc;
-  if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, BLOCK_N))) return rc;
+  if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN, f16))) return rc;
+  if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, BLOCK_N, f16))) return rc;
   if (a.x2) {
-    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N))) return rc;
+    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, p.TW, p.TH, p.TN, 0))) return rc;
+    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N, 0))) return rc;
   } else {
     tmA2 = tmA; tmB2 = tmB;
   }
   if (!a.y_nchw_f32) {
-    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, p.TW, p.TH, p.TN, 0))) return rc;
   } else {
     tmY = tmA;
   }
@@ -404,7 +412,7 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
 extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
   using namespace fidm;
   FIDM_REQUIRE(a && a->x && a->w && a->y, FIDM_E_BADARG, "conv_tc: null x/w/y");
-  FIDM_REQUIRE(a->dtype == FIDM_BF16, FIDM_E_BADARG, "conv_tc: dtype must be bf16");
+  FIDM_REQUIRE(a->dtype == FIDM_BF16 || a->dtype == FIDM_F16, FIDM_E_BADARG, "conv_tc: dtype must be bf16 or f16");
   FIDM_REQUIRE(a->stride == 1 && (a->ksize == 1 || a->ksize == 3), FIDM_E_SHAPE, "conv_tc: only stride 1, ksize 1|3");
   FIDM_REQUIRE(a->cin % 64 == 0 && a->cin > 0, FIDM_E_SHAPE, "conv_tc: cin %d must be a multiple of 64", a->cin);
   FIDM_REQUIRE(a->cout % 16 == 0, FIDM_E_SHAPE, "conv_tc: cout %d must be a multiple of 16", a->cout);

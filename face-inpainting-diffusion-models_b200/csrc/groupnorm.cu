@@ -7,8 +7,9 @@
 //
 // Thread mapping (both passes): a thread owns one VEC-wide channel vector and walks pixels, so a
 // warp reads consecutive 16-byte vectors of one pixel (fully coalesced) and keeps its per-channel
-// affine coefficients in registers.  Statistics are accumulated in fp32 per thread, reduced per
-// group in shared memory, and added to the [batch][groups][2] workspace in double precision.
+// affine coefficients in registers.  Statistics are accumulated in fp32 per thread, then reduced in
+// double precision in a fixed order (block partials, folded by the last block of each image to finish):
+// no floating-point atomics, so the result is bit-reproducible.
 #include "common.cuh"
 
 namespace fidm {
@@ -20,17 +21,17 @@ struct GnParams {
   int pix_per_blk; // pixels (of the iteration space) per block
 };
 
+// Pass 1: per-block partial (sum, sum of squares) of every group, reduced in a FIXED order (no
+// atomics) so that results are bit-reproducible run to run.  partials: [batch][chunks][groups][2].
 template <typename T, int VEC>
-__global__ void gn_stats_kernel(const GnParams p) {
+__global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials, int* __restrict__ counters) {
   const fidm_gn_args& a = p.a;
-  __shared__ float red[64][2];
+  extern __shared__ float red[];           // [blockDim][2]
   const int n = blockIdx.y;
   const int hw = a.height * a.width;
   const int v = threadIdx.x % p.cv;
   const int pl = threadIdx.x / p.cv;
   const int cpg = a.channels / a.groups;
-  for (int i = threadIdx.x; i < a.groups; i += blockDim.x) red[i][0] = red[i][1] = 0.0f;
-  __syncthreads();
   const int p0 = blockIdx.x * p.pix_per_blk;
   const int p1 = min(hw, p0 + p.pix_per_blk);
   const T* base = reinterpret_cast<const T*>(a.x) + (long long)n * hw * a.ld_x + v * VEC;
@@ -44,21 +45,91 @@ __global__ void gn_stats_kernel(const GnParams p) {
       ss = fmaf(f[i], f[i], ss);
     }
   }
-  const int g = (v * VEC) / cpg;
-  atomicAdd(&red[g][0], s);
-  atomicAdd(&red[g][1], ss);
+  red[2 * threadIdx.x] = s;
+  red[2 * threadIdx.x + 1] = ss;
   __syncthreads();
-  for (int i = threadIdx.x; i < a.groups * 2; i += blockDim.x)
-    atomicAdd(&a.stats[((long long)n * a.groups) * 2 + i], (double)red[i >> 1][i & 1]);
+  // group g owns vectors [g*vpg, (g+1)*vpg) of every pixel lane
+  const int vpg = cpg / VEC;
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    double ds = 0.0, dss = 0.0;
+    for (int l = 0; l < p.ppi; ++l)
+      for (int k = 0; k < vpg; ++k) {
+        const int t = l * p.cv + g * vpg + k;
+        ds += (double)red[2 * t];
+        dss += (double)red[2 * t + 1];
+      }
+    double* o = partials + (((long long)n * gridDim.x + blockIdx.x) * a.groups + g) * 2;
+    o[0] = ds;
+    o[1] = dss;
+  }
+  // The last block of image n to finish folds all partials of that image, in a fixed order, into
+  // (mean, rstd): deterministic, and no separate finalize launch.
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&counters[n], 1);
+    is_last = (done == (int)gridDim.x - 1);
+    if (is_last) counters[n] = 0;             // re-arm for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  __syncthreads();
+  // slice j of the block sums chunks j, j+S, ... of group g (4 independent loads in flight), then the
+  // S slice totals of each group are added in slice order: a fixed summation tree.
+  const int chunks = gridDim.x;
+  const int G = a.groups;
+  const int S = max(1, min((int)blockDim.x / G, 8));
+  double* red2 = reinterpret_cast<double*>(red);      // [S][G][2] doubles; red[] holds >= 2*blockDim floats
+  const int g = threadIdx.x % G, j = threadIdx.x / G;
+  if (j < S) {
+    double ds = 0.0, dss = 0.0;
+    const double* q = partials + ((long long)n * chunks * G + g) * 2;
+    int c = j;
+    for (; c + 3 * S < chunks; c += 4 * S) {
+      const double2 v0 = __ldcg(reinterpret_cast<const double2*>(q + (long long)c * G * 2));
+      const double2 v1 = __ldcg(reinterpret_cast<const double2*>(q + (long long)(c + S) * G * 2));
+      const double2 v2 = __ldcg(reinterpret_cast<const double2*>(q + (long long)(c + 2 * S) * G * 2));
+      const double2 v3 = __ldcg(reinterpret_cast<const double2*>(q + (long long)(c + 3 * S) * G * 2));
+      ds += v0.x; dss += v0.y; ds += v1.x; dss += v1.y; ds += v2.x; dss += v2.y; ds += v3.x; dss += v3.y;
+    }
+    for (; c < chunks; c += S) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(q + (long long)c * G * 2));
+      ds += v.x; dss += v.y;
+    }
+    red2[(j * G + g) * 2] = ds;
+    red2[(j * G + g) * 2 + 1] = dss;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    double ds = 0.0, dss = 0.0;
+    for (int k = 0; k < S; ++k) {
+      ds += red2[(k * G + g) * 2];
+      dss += red2[(k * G + g) * 2 + 1];
+    }
+    const double count = (double)cpg * hw;
+    const double mean = ds / count;
+    double var = dss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* mr = reinterpret_cast<float*>(a.stats) + ((long long)n * G + g) * 2;
+    mr[0] = (float)mean;
+    mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
 }
 
 template <bool FAST>
 __device__ __forceinline__ float silu_f(float v) {
-  if (FAST) return __fdividef(v, 1.0f + __expf(-v));
+  if (FAST) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx) instead of ex2 + rcp
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   return v / (1.0f + expf(-v));
 }
 
-template <typename T, int VEC, int RESAMPLE>
+template <typename T, typename TY, int VEC, int RESAMPLE>
 __global__ void gn_apply_kernel(const GnParams p) {
   const fidm_gn_args& a = p.a;
   constexpr bool FAST = (sizeof(T) == 2);
@@ -76,14 +147,8 @@ __global__ void gn_apply_kernel(const GnParams p) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { A[i] = 1.0f; B[i] = 0.0f; }
   } else {
-    const double cnt = (double)cpg * hw;
-    const double s = a.stats[((long long)n * a.groups + g) * 2 + 0];
-    const double ss = a.stats[((long long)n * a.groups + g) * 2 + 1];
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    const float meanf = (float)mean;
+    const float* mr = reinterpret_cast<const float*>(a.stats) + ((long long)n * a.groups + g) * 2;
+    const float meanf = mr[0], rstd = mr[1];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float ga = a.gamma ? a.gamma[c0 + i] : 1.0f;
@@ -101,7 +166,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
     }
   }
   const T* xin = reinterpret_cast<const T*>(a.x) + (long long)n * hw * a.ld_x + c0;
-  T* yo = reinterpret_cast<T*>(a.y);
+  TY* yo = reinterpret_cast<TY*>(a.y);
   T* yr = reinterpret_cast<T*>(a.y_raw);
 
   if (RESAMPLE == FIDM_RESAMPLE_NONE) {
@@ -114,7 +179,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
         float y = fmaf(f[i], A[i], B[i]);
         f[i] = a.silu ? silu_f<FAST>(y) : y;
       }
-      store_vec<T, VEC>(yo + ((long long)n * hw + px) * a.ld_y + c0, f);
+      store_vec<TY, VEC>(yo + ((long long)n * hw + px) * a.ld_y + c0, f);
     }
   } else if (RESAMPLE == FIDM_RESAMPLE_DOWN) {
     const int Ho = H / 2, Wo = W / 2, ohw = Ho * Wo;
@@ -141,7 +206,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
         acc[i] *= 0.25f;
         raw[i] *= 0.25f;
       }
-      store_vec<T, VEC>(yo + ((long long)n * ohw + px) * a.ld_y + c0, acc);
+      store_vec<TY, VEC>(yo + ((long long)n * ohw + px) * a.ld_y + c0, acc);
       if (yr) store_vec<T, VEC>(yr + ((long long)n * ohw + px) * a.ld_raw + c0, raw);
     }
   } else {  // nearest 2x up: one input pixel feeds four outputs
@@ -159,14 +224,14 @@ __global__ void gn_apply_kernel(const GnParams p) {
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const long long op = (long long)n * ohw + (long long)(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-        store_vec<T, VEC>(yo + op * a.ld_y + c0, y);
+        store_vec<TY, VEC>(yo + op * a.ld_y + c0, y);
         if (yr) store_vec<T, VEC>(yr + op * a.ld_raw + c0, f);
       }
     }
   }
 }
 
-template <typename T, int VEC>
+template <typename T, typename TY, int VEC>
 static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
   GnParams p;
   p.a = a;
@@ -187,24 +252,33 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
   };
   int chunks;
   if (!a.skip_norm) {
-    FIDM_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * a.batch * a.groups, st));
+    // workspace: [batch*groups*2] floats (mean, rstd) padded to doubles, then the per-block partials
+    double* partials = a.stats + (long long)a.batch * a.groups;
     chunks = plan(hw);
-    gn_stats_kernel<T, VEC><<<dim3(chunks, a.batch), threads, 0, st>>>(p);
+    const int cap = FIDM_GN_MAX_BLOCKS / a.batch > 0 ? FIDM_GN_MAX_BLOCKS / a.batch : 1;
+    if (chunks > cap) {
+      p.pix_per_blk = (hw + cap - 1) / cap;
+      chunks = (hw + p.pix_per_blk - 1) / p.pix_per_blk;
+    }
+    const long long blocks_cap = (FIDM_GN_MAX_BLOCKS > a.batch ? FIDM_GN_MAX_BLOCKS : a.batch) + a.batch;
+    int* counters = reinterpret_cast<int*>(partials + blocks_cap * a.groups * 2);
+    gn_stats_kernel<T, VEC><<<dim3(chunks, a.batch), threads, sizeof(float) * 2 * threads + 8 * 64 * 2 * sizeof(double), st>>>(
+        p, partials, counters);
     FIDM_CHECK_LAUNCH("groupnorm stats");
   }
   chunks = plan(it_hw);
   dim3 grid(chunks, a.batch);
   if (a.resample == FIDM_RESAMPLE_NONE)
-    gn_apply_kernel<T, VEC, FIDM_RESAMPLE_NONE><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_NONE><<<grid, threads, 0, st>>>(p);
   else if (a.resample == FIDM_RESAMPLE_DOWN)
-    gn_apply_kernel<T, VEC, FIDM_RESAMPLE_DOWN><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_DOWN><<<grid, threads, 0, st>>>(p);
   else
-    gn_apply_kernel<T, VEC, FIDM_RESAMPLE_UP><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_UP><<<grid, threads, 0, st>>>(p);
   FIDM_CHECK_LAUNCH("groupnorm apply");
   return 0;
 }
 
-template <typename T>
+template <typename T, typename TY>
 static int dispatch_vec(const fidm_gn_args& a, cudaStream_t st) {
   const int cpg = a.channels / a.groups;
   constexpr int MAXV = 16 / sizeof(T);  // 16-byte vectors
@@ -215,10 +289,10 @@ static int dispatch_vec(const fidm_gn_args& a, cudaStream_t st) {
     if (a.y_raw) ok = ok && (a.ld_raw % v == 0) && ((uintptr_t)a.y_raw % bytes == 0);
     return ok;
   };
-  if (MAXV >= 8 && aligned(8)) return launch_gn<T, 8>(a, st);
-  if (aligned(4)) return launch_gn<T, 4>(a, st);
-  if (aligned(2)) return launch_gn<T, 2>(a, st);
-  return launch_gn<T, 1>(a, st);
+  if (MAXV >= 8 && aligned(8)) return launch_gn<T, TY, 8>(a, st);
+  if (aligned(4)) return launch_gn<T, TY, 4>(a, st);
+  if (aligned(2)) return launch_gn<T, TY, 2>(a, st);
+  return launch_gn<T, TY, 1>(a, st);
 }
 
 }  // namespace fidm
@@ -234,7 +308,15 @@ extern "C" int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t str
   if (a->resample == FIDM_RESAMPLE_DOWN)
     FIDM_REQUIRE(a->height % 2 == 0 && a->width % 2 == 0, FIDM_E_SHAPE, "groupnorm: odd size for 2x pooling");
   if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "groupnorm: ld_ss < 2*channels");
-  if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16>(*a, (cudaStream_t)stream);
-  if (a->dtype == FIDM_F32) return dispatch_vec<float>(*a, (cudaStream_t)stream);
+  if (a->dtype == FIDM_BF16 && a->y_dtype == FIDM_F16) return dispatch_vec<__nv_bfloat16, __half>(*a, (cudaStream_t)stream);
+  FIDM_REQUIRE(a->y_dtype == a->dtype, FIDM_E_BADARG, "groupnorm: y_dtype %d not supported with dtype %d", a->y_dtype, a->dtype);
+  if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(*a, (cudaStream_t)stream);
+  if (a->dtype == FIDM_F32) return dispatch_vec<float, float>(*a, (cudaStream_t)stream);
   FIDM_REQUIRE(false, FIDM_E_BADARG, "groupnorm: bad dtype %d", a->dtype);
+}
+
+extern "C" int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups) {
+  const long long blocks = (FIDM_GN_MAX_BLOCKS > batch ? FIDM_GN_MAX_BLOCKS : batch) + batch;
+  // (mean, rstd) floats | per-block partial sums | per-image completion counters (must start at zero)
+  return (int64_t)sizeof(double) * ((long long)batch * groups + blocks * groups * 2 + (batch + 1) / 2 + 1);
 }

@@ -27,6 +27,46 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
 }
 
+// Fast path for the network input (<= 16 channels written, e.g. the 9-channel inpainting stem padded
+// to 64: channels >= c_pad are zero-filled once at allocation and never touched again).
+template <typename T>
+__global__ void __launch_bounds__(256) pack16_kernel(const PackParams p) {
+  const fidm_pack_args& a = p.a;
+  const long long total = (long long)a.batch * a.hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.hw);
+    const int px = (int)(i % a.hw);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.0f;
+    int c = 0;
+    for (int s = 0; s < a.n_src; ++s) {
+      const float* src = a.src[s] + (long long)b * a.src_channels[s] * a.hw + px;
+      for (int k = 0; k < a.src_channels[s]; ++k) {
+        const float f = src[(long long)k * a.hw];
+        for (int r = 0; r < a.src_repeat[s]; ++r) {
+          const int cc = c + r * a.src_channels[s] + k;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q == cc) v[q] = f;
+        }
+      }
+      c += a.src_channels[s] * a.src_repeat[s];
+    }
+    T* dst = reinterpret_cast<T*>(a.dst) + i * a.ld_dst;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { lo[q] = v[q]; hi[q] = v[8 + q]; }
+    if (sizeof(T) == 2) {
+      store_vec<T, 8>(dst, lo);
+      if (a.c_pad > 8) store_vec<T, 8>(dst + 8, hi);
+    } else {
+      for (int q = 0; q < a.c_pad; ++q) dst[q] = from_f32<T>(v[q]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_kernel(const T* __restrict__ src, int ld, float* __restrict__ dst,
                                                       int batch, int hw, int channels) {
@@ -79,8 +119,19 @@ extern "C" int fidm_pack_nchw_to_nhwc(const fidm_pack_args* a, fidm_stream_t str
   PackParams p;
   p.a = *a;
   const unsigned g = grid_for((long long)a->batch * a->hw);
+  if (a->c_pad <= 16 && (a->c_pad % 8 == 0) && a->ld_dst % 8 == 0 && (uintptr_t)a->dst % 16 == 0 &&
+      a->dst_dtype != FIDM_F32) {
+    if (a->dst_dtype == FIDM_BF16)
+      pack16_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+    else
+      pack16_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+    FIDM_CHECK_LAUNCH("pack_nchw_to_nhwc");
+    return 0;
+  }
   if (a->dst_dtype == FIDM_BF16)
     pack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+  else if (a->dst_dtype == FIDM_F16)
+    pack_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>(p);
   else
     pack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(p);
   FIDM_CHECK_LAUNCH("pack_nchw_to_nhwc");
@@ -94,6 +145,8 @@ extern "C" int fidm_unpack_nhwc_to_nchw(const void* src, int32_t src_dtype, int3
   const unsigned g = grid_for((long long)batch * hw);
   if (src_dtype == FIDM_BF16)
     unpack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, dst, batch, hw, channels);
+  else if (src_dtype == FIDM_F16)
+    unpack_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld_src, dst, batch, hw, channels);
   else
     unpack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, dst, batch, hw, channels);
   FIDM_CHECK_LAUNCH("unpack_nhwc_to_nchw");
@@ -108,6 +161,8 @@ extern "C" int fidm_repack_weight_oihw_to_krsc(const float* w, void* dst, int32_
   const unsigned g = grid_for((long long)cout_pad * ksize * ksize * cin_pad);
   if (dst_dtype == FIDM_BF16)
     repack_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, cout, cin, ksize, cout_pad, cin_pad);
+  else if (dst_dtype == FIDM_F16)
+    repack_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, cout, cin, ksize, cout_pad, cin_pad);
   else
     repack_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(w, (float*)dst, cout, cin, ksize, cout_pad, cin_pad);
   FIDM_CHECK_LAUNCH("repack_weight");

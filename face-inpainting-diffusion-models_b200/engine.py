@@ -4,7 +4,7 @@ The reference evaluates the UNet as ~700 eager ATen launches on NCHW fp32 tensor
 (`unet.py:154-173`).  Here the topology (`arch.py`) is compiled once per (batch, H, W) into a flat
 list of C-ABI kernel calls on NHWC activations:
 
-  * weights are repacked once: OIHW fp32 -> KRSC bf16 (stem Cin 9 -> 64, head Cout 6 -> 16);
+  * weights are repacked once: OIHW fp32 -> KRSC 16-bit (stem Cin 9 -> 64, head Cout 6 -> 16);
   * `torch.cat([h, hs.pop()], 1)` (`unet.py:170`) never runs: every producer of `h` / `hs[i]` writes
     straight into its channel slice of a pre-planned concat buffer (pixel stride `ld`);
   * GroupNorm+SiLU(+scale/shift)(+2x resample) is one K2 call, conv+bias+emb+residual(+1x1 skip)
@@ -12,11 +12,14 @@ list of C-ABI kernel calls on NHWC activations:
   * the list is captured into a CUDA graph after one eager warm-up, so an evaluation is a single
     graph launch (no Python, no per-kernel launch latency).
 
-precision "bf16": tcgen05 tensor-core kernels, bf16 storage, fp32 accumulate / statistics / softmax.
+precision "bf16": tcgen05 tensor-core kernels, fp32 accumulate / statistics / softmax; the residual stream,
+                  qkv and attention tensors are bf16, the normalized conv operands (GroupNorm outputs) and
+                  the weights they multiply are fp16 (same tensor rate, 8x smaller rounding error).
 precision "fp32": FFMA verification mode (north star: eps within rel-L2 1e-5 of the reference).
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -50,17 +53,18 @@ class _Pool:
         self.free = {}
         self.all = []
 
-    def get(self, B, H, W, Cn):
-        key = (B, H, W, Cn)
+    def get(self, B, H, W, Cn, dtype=None):
+        dtype = dtype or self.dtype
+        key = (B, H, W, Cn, dtype)
         lst = self.free.setdefault(key, [])
         if lst:
             return lst.pop()
-        t = torch.empty(B, H, W, Cn, device=self.device, dtype=self.dtype)
+        t = torch.empty(B, H, W, Cn, device=self.device, dtype=dtype)
         self.all.append(t)
         return t
 
     def put(self, t):
-        self.free.setdefault(tuple(t.shape), []).append(t)
+        self.free.setdefault(tuple(t.shape) + (t.dtype,), []).append(t)
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.all)
@@ -68,6 +72,11 @@ class _Pool:
 
 STEM_CIN_PAD = 64
 HEAD_COUT_PAD = 16
+
+
+def tc_eligible(cin, cout, stride=1, head=False):
+    """Shapes the tcgen05 conv kernel takes (fidm_conv2d_nhwc_bf16)."""
+    return stride == 1 and cin % 64 == 0 and (cout % 64 == 0 or (head and cout == 16))
 
 
 class Weights:
@@ -78,20 +87,30 @@ class Weights:
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.code = L.dtype_code(self.dtype)
         self.conv = {}      # name -> (krsc weight, bias fp32, cin_pad, cout_pad, ksize)
+        # In "bf16" mode the *normalized* conv operands (GroupNorm outputs, the packed network input) and
+        # the weights they meet are stored as fp16: same tcgen05 rate, 11-bit instead of 8-bit mantissa,
+        # and their range is bounded by the normalisation.  The unnormalized residual stream, the qkv /
+        # attention tensors and everything they are multiplied with stay bf16.
+        self.norm_dtype = torch.float16 if precision == "bf16" else torch.float32
+        if precision == "bf16" and os.environ.get("FIDM_NORM_DTYPE", "fp16") == "bf16":
+            self.norm_dtype = torch.bfloat16          # A/B switch: pure-bf16 operands
         self.vec = {}       # name -> fp32 vector (GroupNorm gamma/beta)
         lib = L.lib()
 
         def f32(name):
             return sd[name].detach().to(device=device, dtype=torch.float32).contiguous()
 
-        def conv(name, cin_pad=None, cout_pad=None, extra_bias=None):
+        def conv(name, cin_pad=None, cout_pad=None, extra_bias=None, normalized=False, stride=1, head=False):
             w = f32(name + ".weight")
             if w.dim() == 3:                      # Conv1d k=1 (nn.py:252,254)
                 w = w.unsqueeze(-1)
             cout, cin, ks, _ = w.shape
             cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
-            dst = torch.empty(cout_pad, ks, ks, cin_pad, device=device, dtype=self.dtype)
-            L.check(lib.fidm_repack_weight_oihw_to_krsc(L.ptr(w), L.ptr(dst), self.code, cout, cin, ks,
+            wdt = self.dtype
+            if normalized and precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, head):
+                wdt = self.norm_dtype
+            dst = torch.empty(cout_pad, ks, ks, cin_pad, device=device, dtype=wdt)
+            L.check(lib.fidm_repack_weight_oihw_to_krsc(L.ptr(w), L.ptr(dst), L.dtype_code(wdt), cout, cin, ks,
                                                         cout_pad, cin_pad, L.stream()), "repack " + name)
             b = torch.zeros(cout_pad, device=device, dtype=torch.float32)
             b[:cout] = f32(name + ".bias")
@@ -109,16 +128,16 @@ class Weights:
         for layer in all_layers(topo):
             n = layer.name
             if layer.kind == "stem":
-                conv(n, cin_pad=STEM_CIN_PAD)
+                conv(n, cin_pad=STEM_CIN_PAD, normalized=True)
             elif layer.kind == "res":
                 norm(n + ".in_layers.0")
-                conv(n + ".in_layers.2")
+                conv(n + ".in_layers.2", normalized=True)
                 norm(n + ".out_layers.0")
                 if layer.skip == "identity":
-                    conv(n + ".out_layers.3")
+                    conv(n + ".out_layers.3", normalized=True)
                 else:
                     conv(n + ".skip_connection")
-                    conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"))
+                    conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"), normalized=True)
                 w = f32(n + ".emb_layers.1.weight")
                 emb_w.append(w)
                 emb_b.append(f32(n + ".emb_layers.1.bias"))
@@ -126,14 +145,14 @@ class Weights:
                 off += w.shape[0]
             elif layer.kind == "attn":
                 norm(n + ".norm")
-                conv(n + ".qkv")
+                conv(n + ".qkv", normalized=True)
                 conv(n + ".proj_out")
             elif layer.kind == "down" and layer.use_conv:
-                conv(n + ".op")
+                conv(n + ".op", stride=2)
             elif layer.kind == "up" and layer.use_conv:
                 conv(n + ".conv")
         norm("out.0")
-        conv("out.2", cout_pad=HEAD_COUT_PAD)
+        conv("out.2", cout_pad=HEAD_COUT_PAD, normalized=True, head=True)
         self.emb_total = off
         self.emb_w = torch.cat(emb_w, 0).contiguous()
         self.emb_b = torch.cat(emb_b, 0).contiguous()
@@ -164,10 +183,10 @@ class Plan:
         self.lib = lib
 
         # ---- static inputs / outputs
-        self.x_in = torch.zeros(B, H, W, STEM_CIN_PAD, device=dev, dtype=dt)
+        self.x_in = torch.zeros(B, H, W, STEM_CIN_PAD, device=dev, dtype=weights.conv["input_blocks.0.0"][0].dtype)
         self.t_in = torch.zeros(B, device=dev, dtype=torch.float32)
         self.out = torch.empty(B, topo.out_channels, H, W, device=dev, dtype=torch.float32)
-        self.stats = torch.zeros(B * 32 * 2, device=dev, dtype=torch.float64)
+        self.stats = torch.zeros(lib.fidm_groupnorm_workspace_bytes(B, 32) // 8, device=dev, dtype=torch.float64)
 
         # ---- K5: timestep path
         self.temb = torch.empty(B, mc, device=dev, dtype=torch.float32)
@@ -217,7 +236,7 @@ class Plan:
                 dst = self._new(self.H, self.W, blk.cout)
             x = self._block(blk, full, dst)
         # ---- head: out = conv3x3(SiLU(GN(h)))  (unet.py:148-152,173)
-        a = self._new(x.H, x.W, x.channels)
+        a = self._new(x.H, x.W, x.channels, self._wdtype("out.2"))
         self._gn(x, a, "out.0", silu=True)
         self._conv("out.2", a, None, nchw_out=self.out, cout_valid=topo.out_channels)
 
@@ -229,8 +248,12 @@ class Plan:
     def _op(self, fn, *args):
         self.ops.append((fn, args))
 
-    def _new(self, H, W, Cn):
-        return Ref(self.pool.get(self.B, H, W, Cn), 0, Cn, H, W)
+    def _new(self, H, W, Cn, dtype=None):
+        return Ref(self.pool.get(self.B, H, W, Cn, dtype), 0, Cn, H, W)
+
+    def _wdtype(self, name):
+        """dtype of the weights of conv `name` == dtype its (normalized) input operand must have."""
+        return self.w.conv[name][0].dtype
 
     def _release(self, ref):
         self.pool.put(ref.storage)
@@ -238,7 +261,8 @@ class Plan:
     def _gn(self, x, y, name, silu, scale_shift=None, resample=L.RESAMPLE_NONE, y_raw=None, skip_norm=False):
         w = self.w
         a = L.GnArgs()
-        a.dtype, a.batch, a.height, a.width, a.channels, a.groups = w.code, self.B, x.H, x.W, x.channels, 32
+        a.dtype, a.y_dtype = L.dtype_code(x.storage.dtype), L.dtype_code(y.storage.dtype)
+        a.batch, a.height, a.width, a.channels, a.groups = self.B, x.H, x.W, x.channels, 32
         a.eps = 1e-5
         a.x, a.ld_x = x.ptr, x.ld
         if not skip_norm:
@@ -261,7 +285,8 @@ class Plan:
         wt, bias, cin_pad, cout_pad, ks = w.conv[name]
         assert x.channels == cin_pad, (name, x.channels, cin_pad)
         a = L.ConvArgs()
-        a.dtype, a.batch, a.height, a.width = w.code, self.B, x.H, x.W
+        assert x.storage.dtype == wt.dtype, (name, x.storage.dtype, wt.dtype)
+        a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, x.H, x.W
         a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
         a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
         if x2 is not None:
@@ -279,9 +304,9 @@ class Plan:
             a.y, a.ld_y = y.ptr, y.ld
         a.cout_valid = cout_valid or cout_pad
         self.keep.append(a)
-        tc_ok = (w.precision == "bf16" and stride == 1 and cin_pad % 64 == 0 and
-                 (cout_pad % 64 == 0 or (nchw_out is not None and cout_pad == 16 and residual is None)) and
+        tc_ok = (w.precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
                  (x2 is None or x2.channels % 64 == 0))
+        assert tc_ok or wt.dtype != torch.float16
         fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
         self._op(fn, C.byref(a))
 
@@ -331,14 +356,14 @@ class Plan:
             H, W, mode = H // 2, W // 2, L.RESAMPLE_DOWN
         else:
             mode = L.RESAMPLE_NONE
-        a1 = self._new(H, W, layer.cin)
+        a1 = self._new(H, W, layer.cin, self._wdtype(n + ".in_layers.2"))
         xr = self._new(H, W, layer.cin) if mode != L.RESAMPLE_NONE else None
         self._gn(x, a1, n + ".in_layers.0", silu=True, resample=mode, y_raw=xr)
         h = self._new(H, W, layer.cout)
         off = w.emb_off[n]
         self._conv(n + ".in_layers.2", a1, h, row_add=None if self.ssn else off)
         self._release(a1)
-        a2 = self._new(H, W, layer.cout)
+        a2 = self._new(H, W, layer.cout, self._wdtype(n + ".out_layers.3"))
         self._gn(h, a2, n + ".out_layers.0", silu=True, scale_shift=off if self.ssn else None)
         self._release(h)
         y = dst if dst is not None else self._new(H, W, layer.cout)
@@ -355,7 +380,7 @@ class Plan:
     def _attn(self, layer, x, dst):
         """AttentionBlock._forward (nn.py:259-265)."""
         n, Cn = layer.name, layer.channels
-        a = self._new(x.H, x.W, Cn)
+        a = self._new(x.H, x.W, Cn, self._wdtype(n + ".qkv"))
         self._gn(x, a, n + ".norm", silu=False)
         qkv = self._new(x.H, x.W, 3 * Cn)
         self._conv(n + ".qkv", a, qkv)
@@ -418,7 +443,7 @@ class Plan:
         return self.out
 
     def n_launches(self):
-        """Kernel launches per evaluation (groupnorm = stats + apply; memset nodes not counted)."""
+        """Kernel launches per evaluation (groupnorm = stats + apply)."""
         n = 0
         for fn, args in self.ops:
             if fn is self.lib.fidm_groupnorm_silu_nhwc:

@@ -78,10 +78,11 @@ class InpaintingModelFn:
         if masked_image is None or mask is None:
             if gt is None or gt_keep_mask is None:
                 raise ValueError("Ground truth and mask required for inpainting")
-            key = (gt.data_ptr(), gt_keep_mask.data_ptr(), gt._version, gt_keep_mask._version)
-            if key != self._key:
+            # the cache holds references, so identity (not an address that could be recycled) is compared
+            k = self._key
+            if k is None or k[0] is not gt or k[1] is not gt_keep_mask or k[2:] != (gt._version, gt_keep_mask._version):
                 self._cond = (gt * gt_keep_mask + torch.zeros_like(gt) * (1 - gt_keep_mask), 1 - gt_keep_mask)
-                self._key = key
+                self._key = (gt, gt_keep_mask, gt._version, gt_keep_mask._version)
             masked_image, mask = self._cond
         return self.model(x, t, masked_image=masked_image, mask=mask)
 

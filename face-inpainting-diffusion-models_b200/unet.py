@@ -135,8 +135,10 @@ class UNetModel(nn.Module):
             t = t.detach().to(torch.float32).contiguous()
             keep.append(t)
             a.src[i], a.src_channels[i], a.src_repeat[i] = t.data_ptr(), c, r
-        a.dst, a.dst_dtype = plan.x_in.data_ptr(), plan.w.code
-        a.ld_dst, a.c_pad = STEM_CIN_PAD, STEM_CIN_PAD
+        a.dst, a.dst_dtype = plan.x_in.data_ptr(), L.dtype_code(plan.x_in.dtype)
+        total_c = sum(c * r for _, c, r in sources)
+        # only the first 16 channels are rewritten per call; x_in was zero-filled at allocation
+        a.ld_dst, a.c_pad = STEM_CIN_PAD, (16 if total_c <= 16 else STEM_CIN_PAD)
         L.check(L.lib().fidm_pack_nchw_to_nhwc(a, L.stream()), "pack")
         plan.t_in.copy_(timesteps.detach().to(device=plan.t_in.device, dtype=torch.float32), non_blocking=True)
         out = plan.run()

@@ -29,6 +29,7 @@ extern "C" {
 
 #define FIDM_F32  0
 #define FIDM_BF16 1
+#define FIDM_F16  2   /* normalized conv operands (GroupNorm outputs) and their weights: 11-bit mantissa */
 
 #define FIDM_E_BADARG   (-1)
 #define FIDM_E_SHAPE    (-2)   /* shape not supported by this kernel (caller picks another entry) */
@@ -138,11 +139,15 @@ int fidm_linear_small(const float* x, const void* w, int32_t w_dtype, const floa
  * Replaces nn.GroupNorm(32,C) + nn.SiLU (nn.py:46-48,151-152,173-174; unet.py:149-150; attention
  * norm nn.py:251), the scale/shift modulation nn.py:203-206 and the resampling of up/down
  * ResBlocks nn.py:190-195 (h_upd on the activated tensor and x_upd on the raw tensor).
- * `stats` is a caller-provided workspace of batch*groups*2 doubles (sum, sum of squares).
+ * `stats` is a caller-provided workspace of fidm_groupnorm_workspace_bytes(batch, groups) bytes
+ * (per-block partial sums, reduced in a fixed order: results are bit-reproducible).  The workspace must
+ * be zero-initialised once by the caller; the kernel leaves its completion counters at zero.
  * ---------------------------------------------------------------------------------------------- */
+#define FIDM_GN_MAX_BLOCKS 2048
 enum { FIDM_RESAMPLE_NONE = 0, FIDM_RESAMPLE_DOWN = 1, FIDM_RESAMPLE_UP = 2 };
 typedef struct fidm_gn_args {
-  int32_t dtype;                        /* FIDM_BF16 | FIDM_F32, same for x / y / y_raw */
+  int32_t dtype;                        /* FIDM_BF16 | FIDM_F32: x and y_raw */
+  int32_t y_dtype;                      /* dtype of y: = dtype, or FIDM_F16 when dtype is FIDM_BF16 */
   int32_t batch, height, width, channels, groups;
   float eps;
   const void* x; int32_t ld_x;
@@ -154,9 +159,10 @@ typedef struct fidm_gn_args {
                                            nn.py:109,129): no statistics, no affine */
   void* y; int32_t ld_y;                /* activated output (resampled resolution) */
   void* y_raw; int32_t ld_raw;          /* optional: resample(x) without norm (x_upd, nn.py:194) */
-  double* stats;                        /* workspace [batch][groups][2] (unused when skip_norm) */
+  double* stats;                        /* workspace (unused when skip_norm) */
 } fidm_gn_args;
 int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream);
+int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  convolution as implicit GEMM, NHWC activations, KRSC weights ([Cout][kh][kw][Cin]).
@@ -173,7 +179,9 @@ int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream);
  *                            kernel does not take: stride 2, small/odd channel counts).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct fidm_conv_args {
-  int32_t dtype;                        /* of x / w / x2 / w2 / residual / y (unless y_nchw_f32) */
+  int32_t dtype;                        /* of x and w: FIDM_BF16 | FIDM_F16 (tensor-core entry), FIDM_BF16 |
+                                           FIDM_F32 (simt entry).  x2 / w2 / residual / y are bf16 whenever
+                                           dtype is a 16-bit type, fp32 otherwise. */
   int32_t batch, height, width;         /* INPUT spatial size */
   int32_t cin, cout, ksize, stride;     /* ksize 1 or 3 (pad = ksize/2); stride 1 or 2 */
   const void* x; int32_t ld_x;
