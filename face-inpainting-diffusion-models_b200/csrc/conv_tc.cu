@@ -21,6 +21,7 @@
 //   * Persistent CTAs (one per SM), static tile striding; tiles that share an M box are adjacent
 //     so their A boxes hit L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100_primitives.cuh"
@@ -47,20 +48,25 @@ constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;                 // 128 rows x 64 bf16
 constexpr int kStagingBytes = 128 * 128;           // one 128 x 64 bf16 output chunk
 
-template <int BLOCK_N> struct ConvCfg {
-  static constexpr int kBBytes = BLOCK_N * 128;
+// CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cta_group::2) owns a 256 x BLOCK_N tile; each
+// CTA stages its own 128 pixel rows of A and HALF of the weight tile, which cuts the shared-memory traffic
+// per MMA from 48 KB to 32 KB per 64-deep K block -- the 1-CTA kernel is shared-memory-bandwidth bound
+// (48 KB written by TMA + 48 KB read by the tensor core every 512 cycles = 192 B/clk/SM).
+template <int BLOCK_N, int CG> struct ConvCfg {
+  static constexpr int kBRows = BLOCK_N / CG;
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + (kBBytes < 1024 ? 1024 : kBBytes);
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 256 + 1024;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmY, const ConvTcParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,10 +78,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // rank 0 = leader (issues the MMAs)
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile (CG=1) / tile-pair (CG=2) slot
+  const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int taps = p.ksize * p.ksize;
   const int k_iters = taps * p.kc1 + p.kc2;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_blocks;
+  // CG = 2: work items are PAIRS of consecutive M tiles (a phantom tile past the end is zero-filled by
+  // TMA and clipped on store)
+  const int total_tiles = ((m_tiles + CG - 1) / CG) * p.n_blocks;
   const int pad = p.ksize >> 1;
 
   if (warp == 4 && lane == 0) {
@@ -86,16 +97,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 5) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * kEpiWarps); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -103,26 +114,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_blocks, m_blk = tile / p.n_blocks;
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
         const int w0 = (m_blk % p.tiles_w) * p.TW;
         const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
-        const int co0 = n_blk * BLOCK_N;
+        const int co0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;   // this CTA's share of the weight tile
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kABytes + Cfg::kBBytes);
+          if (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], kABytes + Cfg::kBBytes);
+          } else if (cta_rank == 0) {
+            mbar_expect_tx(&full_bar[stage], 2 * (kABytes + Cfg::kBBytes));   // both CTAs' bytes land on the leader
+          } else {
+            mbar_arrive_cluster(&full_bar[stage], 0);
+          }
           if (it < taps * p.kc1) {
             const int tap = it / p.kc1, kc = it - tap * p.kc1;
             const int r = tap / p.ksize, s = tap - r * p.ksize;
-            tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
-            tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+            if (CG == 1) {
+              tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
+              tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+            } else {
+              tma_load_4d_2sm(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
+              tma_load_2d_2sm(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+            }
           } else {
             const int kc = it - taps * p.kc1;
-            tma_load_4d(&tmA2, &full_bar[stage], sa, kc * 64, w0, h0, n0);
-            tma_load_2d(&tmB2, &full_bar[stage], sb, kc * 64, co0);
+            if (CG == 1) {
+              tma_load_4d(&tmA2, &full_bar[stage], sa, kc * 64, w0, h0, n0);
+              tma_load_2d(&tmB2, &full_bar[stage], sb, kc * 64, co0);
+            } else {
+              tma_load_4d_2sm(&tmA2, &full_bar[stage], sa, kc * 64, w0, h0, n0);
+              tma_load_2d_2sm(&tmB2, &full_bar[stage], sb, kc * 64, co0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -130,14 +157,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 5) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       // second-source (raw residual stream) operands are always bf16
-      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(128, BLOCK_N);
-      const uint32_t idesc_main = p.ab_f16 ? umma_idesc_f16(128, BLOCK_N) : idesc_bf16;
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(128 * CG, BLOCK_N);
+      const uint32_t idesc_main = p.ab_f16 ? umma_idesc_f16(128 * CG, BLOCK_N) : idesc_bf16;
       const int main_iters = p.ksize * p.ksize * p.kc1;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -149,12 +176,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t db = umma_desc_sw128(sa + kABytes);
           const uint32_t idesc = it < main_iters ? idesc_main : idesc_bf16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 elements = 32 B) inside the 128-byte swizzle atom
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < 4; ++k) { // 4 x (K = 16 elements = 32 B) inside the 128-byte swizzle atom
+            if (CG == 1) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+            else umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_2sm(&empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);          // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 1) umma_commit(&tmem_full[acc]); else umma_commit_2sm(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -166,8 +197,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (threadIdx.x == 0);
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.n_blocks, m_blk = tile / p.n_blocks;
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
+      const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
       const int w0 = (m_blk % p.tiles_w) * p.TW;
       const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -190,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ch == BLOCK_N / 64 - 1) {       // all TMEM reads of this accumulator are done
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0); }
           }
           const int cbase = co0 + ch * 64;
           float f[64];
@@ -289,10 +320,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -362,9 +393,9 @@ int pick_pixel_box(int W, int H, int* tw, int* th, int* tn) {
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, CG>;
   ConvTcParams p;
   p.B = a.batch; p.H = a.height; p.W = a.width;
   pick_pixel_box(a.width, a.height, &p.TW, &p.TH, &p.TN);
@@ -383,10 +414,10 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
   int rc;
   if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN, f16))) return rc;
-  if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, BLOCK_N, f16))) return rc;
+  if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, Cfg::kBRows, f16))) return rc;
   if (a.x2) {
     if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, p.TW, p.TH, p.TN, 0))) return rc;
-    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N, 0))) return rc;
+    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, Cfg::kBRows, 0))) return rc;
   } else {
     tmA2 = tmA; tmB2 = tmB;
   }
@@ -397,12 +428,28 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    FIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
-  const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmA2, tmB2, tmY, p);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int units = ((m_tiles + CG - 1) / CG) * p.n_blocks;          // tiles (CG=1) or tile pairs (CG=2)
+  const int slots = num_sms() / CG;
+  const int grid = (units < slots ? units : slots) * CG;
+  if (CG == 1) {
+    conv_tc_kernel<BLOCK_N, CG><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmA2, tmB2, tmY, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG>, tmA, tmB, tmA2, tmB2, tmY, p));
+  }
   FIDM_CHECK_LAUNCH("conv_tc");
   return 0;
 }
@@ -427,14 +474,16 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   if (a->cout % 64 != 0 || a->y_nchw_f32) {
     FIDM_REQUIRE(a->y_nchw_f32 && a->cout == 16 && !a->residual, FIDM_E_SHAPE,
                  "conv_tc: cout %d is only supported as the 16-wide fp32-NCHW head", a->cout);
-    return launch_conv_tc<16>(*a, st);
+    return launch_conv_tc<16, 1>(*a, st);
   }
   // Widest N tile that still yields about one tile per SM; narrow tiles for the small low-resolution layers.
   int tw, th, tn;
   pick_pixel_box(a->width, a->height, &tw, &th, &tn);
   const long long m_tiles = (long long)(a->width / tw) * (a->height / th) * ((a->batch + tn - 1) / tn);
   const int want = (num_sms() * 3) / 4;
-  if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want) return launch_conv_tc<256>(*a, st);
-  if (a->cout % 128 == 0 && m_tiles * (a->cout / 128) >= want) return launch_conv_tc<128>(*a, st);
-  return launch_conv_tc<64>(*a, st);
+  static const bool pair_ok = getenv("FIDM_CONV_CTA_PAIR") == nullptr || atoi(getenv("FIDM_CONV_CTA_PAIR")) != 0;
+  if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want)
+    return pair_ok ? launch_conv_tc<256, 2>(*a, st) : launch_conv_tc<256, 1>(*a, st);
+  if (a->cout % 128 == 0 && m_tiles * (a->cout / 128) >= want) return launch_conv_tc<128, 1>(*a, st);
+  return launch_conv_tc<64, 1>(*a, st);
 }

@@ -42,6 +42,8 @@ SHAPES = [
     (1, 64, 64, 64, 256, 3), (1, 64, 64, 256, 512, 1), (1, 128, 128, 64, 64, 3),
     (1, 256, 256, 64, 256, 3), (2, 32, 32, 512, 1536, 1), (4, 8, 8, 1024, 1024, 3),
     (1, 16, 16, 2048, 1024, 3), (8, 64, 64, 128, 256, 3),
+    (37, 16, 24, 64, 256, 3),      # CTA-pair kernel with an ODD number of M tiles (phantom half-tile), W = 24
+    (2, 128, 128, 256, 512, 3),    # CTA-pair kernel, two N blocks
 ]
 
 
