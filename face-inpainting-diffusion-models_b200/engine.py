@@ -169,7 +169,7 @@ class Weights:
 class Plan:
     """Flat kernel schedule + buffers for one (batch, H, W)."""
 
-    def __init__(self, weights: Weights, B, H, W, use_graph=True):
+    def __init__(self, weights: Weights, B, H, W, use_graph=True, out=None):
         self.w, self.B, self.H, self.W = weights, B, H, W
         topo = weights.topo
         dev, dt = weights.device, weights.dtype
@@ -185,7 +185,9 @@ class Plan:
         # ---- static inputs / outputs
         self.x_in = torch.zeros(B, H, W, STEM_CIN_PAD, device=dev, dtype=weights.conv["input_blocks.0.0"][0].dtype)
         self.t_in = torch.zeros(B, device=dev, dtype=torch.float32)
-        self.out = torch.empty(B, topo.out_channels, H, W, device=dev, dtype=torch.float32)
+        self.out = out if out is not None else torch.empty(B, topo.out_channels, H, W, device=dev,
+                                                           dtype=torch.float32)
+        assert self.out.is_contiguous() and self.out.shape[0] == B
         self.stats = torch.zeros(lib.fidm_groupnorm_workspace_bytes(B, 32) // 8, device=dev, dtype=torch.float64)
 
         # ---- K5: timestep path
@@ -418,6 +420,23 @@ class Plan:
         return y
 
     # ------------------------------------------------------------------ execution
+    def load_inputs(self, sources, timesteps, batch_offset=0):
+        """Pack the fp32 NCHW `sources` [(tensor, channels, repeat)] (rows batch_offset .. +B) into the
+        NHWC network input and copy the timesteps."""
+        a = L.PackArgs()
+        hw = self.H * self.W
+        a.batch, a.hw, a.n_src = self.B, hw, len(sources)
+        total_c = 0
+        for i, (t, c, r) in enumerate(sources):
+            a.src[i] = t.data_ptr() + batch_offset * c * hw * 4
+            a.src_channels[i], a.src_repeat[i] = c, r
+            total_c += c * r
+        a.dst, a.dst_dtype = self.x_in.data_ptr(), L.dtype_code(self.x_in.dtype)
+        # only the first 16 channels are rewritten per call; x_in was zero-filled at allocation
+        a.ld_dst, a.c_pad = STEM_CIN_PAD, (16 if total_c <= 16 else STEM_CIN_PAD)
+        L.check(self.lib.fidm_pack_nchw_to_nhwc(a, L.stream()), "pack")
+        self.t_in.copy_(timesteps[batch_offset:batch_offset + self.B], non_blocking=True)
+
     def launch_all(self):
         st = L.stream()
         for fn, args in self.ops:
@@ -451,3 +470,63 @@ class Plan:
             else:
                 n += 1
         return n
+
+
+class PlanGroup:
+    """Two (or more) half-batch plans captured as PARALLEL branches of one CUDA graph.
+
+    The UNet alternates tensor-pipe-bound kernels (K1 conv, K3 attention) with HBM-bound ones (K2
+    GroupNorm).  Samples are independent, so the batch is split into micro-batches whose kernel chains run
+    on separate streams: while one micro-batch is in a convolution the other's GroupNorm blocks co-reside
+    on the same SMs (the conv CTAs use 192 threads and no more than one CTA per SM) and use the idle HBM
+    bandwidth.  Results are identical to the single-plan execution (every kernel is per-sample)."""
+
+    def __init__(self, weights: Weights, B, H, W, parts=2, use_graph=True):
+        assert B % parts == 0
+        self.B, self.H, self.W, self.w = B, H, W, weights
+        b = B // parts
+        self.out = torch.empty(B, weights.topo.out_channels, H, W, device=weights.device, dtype=torch.float32)
+        self.parts = [Plan(weights, b, H, W, use_graph=False, out=self.out[i * b:(i + 1) * b]) for i in range(parts)]
+        self.use_graph = use_graph
+        self.graph = None
+        self.pool = self                         # bench.py reads plan.pool.nbytes()
+
+    def nbytes(self):
+        return sum(p.pool.nbytes() for p in self.parts)
+
+    def n_launches(self):
+        return sum(p.n_launches() for p in self.parts)
+
+    def load_inputs(self, sources, timesteps):
+        for i, p in enumerate(self.parts):
+            p.load_inputs(sources, timesteps, batch_offset=i * p.B)
+
+    def run(self):
+        if not self.use_graph:
+            for p in self.parts:
+                p.launch_all()
+            return self.out
+        if self.graph is None:
+            for p in self.parts:                  # eager warm-up: func attributes, driver entry points
+                p.launch_all()
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                joins = []
+                for p in self.parts[1:]:
+                    side = torch.cuda.Stream()
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        p.launch_all()
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    joins.append(ev)
+                self.parts[0].launch_all()
+                for ev in joins:
+                    main.wait_event(ev)
+            self.graph = g
+        self.graph.replay()
+        return self.out
