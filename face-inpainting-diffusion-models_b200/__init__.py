@@ -10,3 +10,4 @@ from .train_inpainting import (InpaintingModelFn, create_model_and_diffusion,  #
                                sample_with_advanced_inpainting)
 from .unet import DiffusionInpaintingModel, UNetModel  # noqa: F401
 from .utils.schedules import create_gaussian_diffusion, get_named_beta_schedule  # noqa: F401
+from .script_sampler import InpaintingSampler, create_ddim_timestep_sequence  # noqa: F401

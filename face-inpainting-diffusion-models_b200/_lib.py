@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfidm_b200.so")
 F32, BF16, F16 = 0, 1, 2
 COEF_COLS = 20
 STEP_INJECT_ONLY, STEP_UPDATE_ONLY, STEP_UPDATE_INJECT = 0, 1, 2
-SAMPLER_DDPM, SAMPLER_DDIM = 0, 1
+SAMPLER_DDPM, SAMPLER_DDIM, SAMPLER_DDIM_SCRIPT = 0, 1, 2
 MEAN_PREVIOUS_X, MEAN_START_X, MEAN_EPSILON = 0, 1, 2
 VAR_LEARNED, VAR_FIXED, VAR_LEARNED_RANGE = 0, 1, 2
 RESAMPLE_NONE, RESAMPLE_DOWN, RESAMPLE_UP = 0, 1, 2

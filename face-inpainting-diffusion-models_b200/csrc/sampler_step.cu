@@ -70,7 +70,12 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
         }
         // ---- pred_xstart and posterior mean (:267-286)
         float x0, mean;
-        if (a.mean_type == FIDM_MEAN_EPSILON) {
+        if (a.sampler == FIDM_SAMPLER_DDIM_SCRIPT) {
+          // test_inp_ddim_100.py:539-542: pred_x0 = (img - sqrt(1-ab_t) * eps) / sqrt(ab_t)
+          x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c2, mo[i])), c1);
+          if (a.clip_denoised) x0 = clamp1(x0);
+          mean = x0;
+        } else if (a.mean_type == FIDM_MEAN_EPSILON) {
           x0 = __fsub_rn(__fmul_rn(c1, x), __fmul_rn(c2, mo[i]));
           if (a.clip_denoised) x0 = clamp1(x0);
           mean = __fadd_rn(__fmul_rn(k1, x0), __fmul_rn(k2, x));
@@ -86,7 +91,11 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
         mv[i] = mean;
         lv[i] = logvar;
         const float z = need_z ? zz[i] : 0.0f;
-        if (a.sampler == FIDM_SAMPLER_DDIM) {
+        if (a.sampler == FIDM_SAMPLER_DDIM_SCRIPT) {
+          // :551-557  img = sqrt(ab_prev) * x0 + sqrt(1 - ab_prev - sigma^2) * eps_raw + sigma * noise
+          const float mp = __fadd_rn(__fmul_rn(cf[FIDM_C_DDIM_SQRT_ABP], x0), __fmul_rn(cf[FIDM_C_DDIM_DIR], mo[i]));
+          smp[i] = need_z ? __fadd_rn(mp, __fmul_rn(cf[FIDM_C_DDIM_SIGMA], z)) : mp;
+        } else if (a.sampler == FIDM_SAMPLER_DDIM) {
           // eps re-derived from the (clamped) x0 (:470, :316-319), then :479-484
           const float e = __fdiv_rn(__fsub_rn(__fmul_rn(c1, x), x0), c2);
           const float mp = __fadd_rn(__fmul_rn(x0, cf[FIDM_C_DDIM_SQRT_ABP]), __fmul_rn(cf[FIDM_C_DDIM_DIR], e));

@@ -119,7 +119,7 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ K4 launcher
     def _step(self, mode, x, *, t=None, t_inject=None, t_dev=None, model_out=None, z=None, gt=None, keep=None,
               inject_noise=None, ddim=True, eta=0.0, clip=True, cumulative=True, want_sample=False,
-              want_x0=False, want_next=False, want_mean=False, want_logvar=False):
+              want_x0=False, want_next=False, want_mean=False, want_logvar=False, script_table=None):
         L.require_cuda(x, model_out, z, gt, keep, inject_noise)
         B, Cn = x.shape[0], x.shape[1]
         hw = x.numel() // (B * Cn)
@@ -128,11 +128,13 @@ class GaussianDiffusion:
         a.mode = mode
         a.sampler = L.SAMPLER_DDIM if ddim else L.SAMPLER_DDPM
         a.mean_type, a.var_type = _MEAN_CODE[self.model_mean_type], _VAR_CODE[self.model_var_type]
+        if script_table is not None:      # per-step rows of the evaluation scripts' strided DDIM
+            a.sampler = L.SAMPLER_DDIM_SCRIPT
         a.clip_denoised, a.cumulative = int(bool(clip)), int(bool(cumulative))
-        a.num_timesteps = self.num_timesteps
+        a.num_timesteps = self.num_timesteps if script_table is None else script_table.shape[0]
         a.t_update = -1 if t is None else int(t)
         a.t_inject = -1 if t_inject is None else int(t_inject)
-        coef = self._coef(x.device, eta if ddim else 0.0)
+        coef = script_table if script_table is not None else self._coef(x.device, eta if ddim else 0.0)
         keepalive = [coef]
 
         def c(tn, name, shape=None):
@@ -153,6 +155,9 @@ class GaussianDiffusion:
         if mode != L.STEP_INJECT_ONLY:
             model_out = c(model_out, "model_out")
             want_ch = Cn if a.var_type == L.VAR_FIXED else 2 * Cn
+            if script_table is not None and model_out.shape[1] == Cn:
+                a.var_type = L.VAR_FIXED          # scripts accept 3- or 6-channel outputs (:515-520)
+                want_ch = Cn
             assert model_out.shape == (B, want_ch) + tuple(x.shape[2:]), \
                 f"model output shape {tuple(model_out.shape)} != {(B, want_ch) + tuple(x.shape[2:])}"
             a.model_out = L.ptr(model_out)

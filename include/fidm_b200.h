@@ -76,7 +76,11 @@ enum {
   FIDM_C_XPREV_B = 16        /* posterior_mean_coef2/posterior_mean_coef1   (:311-313) */
 };
 enum { FIDM_STEP_INJECT_ONLY = 0, FIDM_STEP_UPDATE_ONLY = 1, FIDM_STEP_UPDATE_INJECT = 2 };
-enum { FIDM_SAMPLER_DDPM = 0, FIDM_SAMPLER_DDIM = 1 };
+enum { FIDM_SAMPLER_DDPM = 0, FIDM_SAMPLER_DDIM = 1,
+       /* the evaluation scripts' strided DDIM update (test_inp_ddim_100.py:539-557): x0 = (x - c5*eps)/c4,
+          x <- (c11*x0 + c12*eps) + c13*z with the RAW eps; coefficient rows are indexed by step, not t:
+          c4 = sqrt(ab_t), c5 = sqrt(1-ab_t), c0/c1 = injection coefficients at ab_prev (:560-574) */
+       FIDM_SAMPLER_DDIM_SCRIPT = 2 };
 enum { FIDM_MEAN_PREVIOUS_X = 0, FIDM_MEAN_START_X = 1, FIDM_MEAN_EPSILON = 2 };
 enum { FIDM_VAR_LEARNED = 0, FIDM_VAR_FIXED = 1, FIDM_VAR_LEARNED_RANGE = 2 };
 

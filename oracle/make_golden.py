@@ -257,10 +257,115 @@ def golden_variants():
     torch.save(res, os.path.join(OUT, "t32_variants.pt"))
 
 
+def _reference_script_methods():
+    """Method bodies of the reference's InpaintingSampler, extracted from the script source (the script
+    imports lpips / skimage / pytorch_fid at module level and cannot be imported here)."""
+    import ast
+    import textwrap
+    import types
+    from tqdm.auto import tqdm
+    path = "/root/reference/code/test_inp_ddim_100.py"
+    src = open(path).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "InpaintingSampler"][0]
+    ns = {"torch": torch, "np": np, "tqdm": tqdm}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("model_fn", "create_ddim_timestep_sequence",
+                                                           "inpainting_ddim_sample_loop", "inpainting_p_sample_loop"):
+            exec(textwrap.dedent(ast.get_source_segment(src, fn)), ns)
+    return ns, types
+
+
+class SeqRandn:
+    """torch.randn / randn_like patched to an explicit (kind, t) sequence."""
+
+    def __init__(self, seq, seed):
+        self.seq, self.i, self.seed = list(seq), 0, seed
+
+    def _next(self, shape):
+        kind, t = self.seq[self.i]
+        self.i += 1
+        return seeded_noise(kind, t, tuple(shape), self.seed)
+
+    def __enter__(self):
+        self._r, self._rl = torch.randn, torch.randn_like
+        torch.randn = lambda *s, **k: self._next(s[0] if len(s) == 1 and not isinstance(s[0], int) else s)
+        torch.randn_like = lambda x, **k: self._next(x.shape)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._r, self._rl
+        assert self.i == len(self.seq), (self.i, len(self.seq))
+
+
+def golden_script_loops():
+    """The evaluation scripts' own loops (strided DDIM, post-step injection) on T64."""
+    import contextlib
+    import io
+    import types as _t
+    from oracle import script_oracle as sor
+    ns, types = _reference_script_methods()
+    model, sd, cfg = build_ref_model("T64", seed=1)
+    data = synth_batch(1, 64, seed=4)
+    gt, masks = data["gt"], data["mask"]
+    shape = (1, 3, 64, 64)
+    out = {}
+    for tag, steps, sched, n_ddim, eta in (("quad1000_ddim20", 1000, "quadratic", 20, 0.0),
+                                           ("cos100_ddim10_eta", 100, "cosine", 10, 0.5)):
+        d = create_gaussian_diffusion(steps=steps, learn_sigma=True, noise_schedule=sched)
+        me = _t.SimpleNamespace(model=model, diffusion=d, args=_t.SimpleNamespace(ddim_timesteps=n_ddim))
+        for name in ("model_fn", "create_ddim_timestep_sequence", "inpainting_ddim_sample_loop", "inpainting_p_sample_loop"):
+            setattr(me, name, types.MethodType(ns[name], me))
+        seq = me.create_ddim_timestep_sequence(steps, n_ddim)
+        assert list(seq) == list(sor.ddim_timestep_sequence(steps, n_ddim))
+        order = [("xT", 0)]
+        for t in seq:
+            if t > 0 and eta > 0:
+                order.append(("step", int(t)))
+            if t > 0:
+                order.append(("inject", int(t)))
+        seed = 31
+        with SeqRandn(order, seed), torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            ref = me.inpainting_ddim_sample_loop(me.model_fn, shape, gt, masks, clip_denoised=True, device="cpu", eta=eta)
+        tab = dor.Tables(get_named_beta_schedule(sched, steps))
+        with torch.no_grad():
+            mine = sor.script_ddim_loop(
+                tab, lambda x, t, gt=None, gt_keep_mask=None: uor.inpaint_forward(sd, cfg, x, t, gt * gt_keep_mask, 1 - gt_keep_mask),
+                shape, gt, masks, n_ddim, eta=eta, x_T=seeded_noise("xT", 0, shape, seed),
+                noise_fn=lambda kind, t: seeded_noise(kind, t, shape, seed))
+        assert torch.equal(ref, mine), tag
+        print("script DDIM", tag, "evals", len(seq), "oracle == reference (bit-exact)")
+        out[tag] = {"steps": steps, "sched": sched, "n_ddim": n_ddim, "eta": eta, "seed_noise": seed,
+                    "seed_weights": 1, "seed_data": 4, "n_evals": len(seq), "final": ref}
+    # DDPM script loop on a short schedule
+    steps, seed = 30, 37
+    d = create_gaussian_diffusion(steps=steps, learn_sigma=True, noise_schedule="cosine")
+    me = _t.SimpleNamespace(model=model, diffusion=d, args=_t.SimpleNamespace(ddim_timesteps=10))
+    for name in ("model_fn", "inpainting_p_sample_loop"):
+        setattr(me, name, types.MethodType(ns[name], me))
+    order = [("xT", 0)]
+    for i in range(steps - 1, -1, -1):
+        order.append(("step", i))
+        if i > 0:
+            order.append(("inject", i))
+    with SeqRandn(order, seed), torch.no_grad():
+        ref = me.inpainting_p_sample_loop(me.model_fn, shape, gt, masks, clip_denoised=True, device="cpu")
+    tab = dor.Tables(get_named_beta_schedule("cosine", steps))
+    with torch.no_grad():
+        mine = sor.script_ddpm_loop(
+            tab, lambda x, t, gt=None, gt_keep_mask=None: uor.inpaint_forward(sd, cfg, x, t, gt * gt_keep_mask, 1 - gt_keep_mask),
+            shape, gt, masks, x_T=seeded_noise("xT", 0, shape, seed), noise_fn=lambda kind, t: seeded_noise(kind, t, shape, seed))
+    assert torch.equal(ref, mine)
+    print("script DDPM-30: oracle == reference (bit-exact)")
+    out["cos30_ddpm"] = {"steps": steps, "sched": "cosine", "seed_noise": seed, "seed_weights": 1, "seed_data": 4, "final": ref}
+    torch.save(out, os.path.join(OUT, "t64_script_loops.pt"))
+
+
 if __name__ == "__main__":
     golden_topology()
     golden_schedules()
     golden_steps()
     golden_t64()
     golden_variants()
+    golden_script_loops()
     print("golden fixtures written to", OUT)

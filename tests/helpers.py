@@ -45,3 +45,36 @@ def psnr(a, b, peak=2.0):
 
 def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+class SeqRandn:
+    """torch.randn / randn_like patched to an explicit [(kind, t), ...] draw sequence."""
+
+    def __init__(self, seq, seed, device="cpu"):
+        self.seq, self.i, self.seed, self.device = list(seq), 0, seed, device
+
+    def _next(self, shape):
+        kind, t = self.seq[self.i]
+        self.i += 1
+        return seeded_noise(kind, t, tuple(shape), self.seed).to(self.device)
+
+    def __enter__(self):
+        self._r, self._rl = torch.randn, torch.randn_like
+        torch.randn = lambda *s, **k: self._next(s[0] if len(s) == 1 and not isinstance(s[0], int) else s)
+        torch.randn_like = lambda x, **k: self._next(x.shape)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._r, self._rl
+
+
+def script_draw_order(seq, eta=0.0, ddpm=False):
+    """RNG draw order of the evaluation scripts' loops (test_inp_ddim_100.py:402-576)."""
+    order = [("xT", 0)]
+    for t in seq:
+        t = int(t)
+        if ddpm or (t > 0 and eta > 0):
+            order.append(("step", t))
+        if t > 0:
+            order.append(("inject", t))
+    return order

@@ -169,3 +169,73 @@ def test_256_eps_matches_oracle(cuda_lib, name, B):
     with torch.no_grad():
         want = uor.inpaint_forward(sd, cfg, x, t, data["masked_image"].cpu(), data["mask"].cpu())
     assert rel_l2(out.cpu(), want) < 1e-2
+
+
+@pytest.mark.parametrize("precision,min_psnr", [("fp32", 60.0), ("bf16", 38.0)])
+def test_script_level_loops_match_reference(cuda_lib, golden_dir, precision, min_psnr):
+    """the CLIs' own loops (strided DDIM with raw eps, post-step fresh-noise injection,
+    DDPM variant, final blend) against outputs of the reference's method bodies."""
+    import fidm_b200 as F
+    from fidm_b200.script_sampler import InpaintingSampler, create_ddim_timestep_sequence
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    from helpers import SeqRandn, script_draw_order
+    gold = torch.load(os.path.join(golden_dir, "t64_script_loops.pt"))
+    cfg = F.CONFIGS["T64"]
+    m = _model(cfg, synth_state_dict(cfg, seed=1), precision)
+    data = synth_batch(1, 64, seed=4, device=DEV)
+    gt, masks = data["gt"], data["mask"]
+    shape = (1, 3, 64, 64)
+    for tag in ("quad1000_ddim20", "cos100_ddim10_eta"):
+        g = gold[tag]
+        d = F.create_gaussian_diffusion(steps=g["steps"], learn_sigma=True, noise_schedule=g["sched"])
+        s = InpaintingSampler(m, d, ddim_timesteps=g["n_ddim"], eta=g["eta"])
+        seq = create_ddim_timestep_sequence(g["steps"], g["n_ddim"])
+        assert len(seq) == g["n_evals"]
+        with SeqRandn(script_draw_order(seq, g["eta"]), g["seed_noise"], device=DEV):
+            out = s.inpainting_ddim_sample_loop(s.model_fn, shape, gt, masks, device=DEV, eta=g["eta"])
+        assert psnr(out.cpu(), g["final"]) >= min_psnr, (tag, precision, psnr(out.cpu(), g["final"]))
+    g = gold["cos30_ddpm"]
+    d = F.create_gaussian_diffusion(steps=g["steps"], learn_sigma=True, noise_schedule=g["sched"])
+    s = InpaintingSampler(m, d, use_ddim=False)
+    with SeqRandn(script_draw_order(range(g["steps"] - 1, -1, -1), ddpm=True), g["seed_noise"], device=DEV):
+        res, _, masked, _ = s.sample_batch(gt, masks)
+    want = g["final"] * masks.cpu() + gt.cpu() * (1 - masks.cpu())
+    assert psnr(res.cpu(), want) >= min_psnr
+    keep = (1 - masks).expand_as(res) == 1
+    assert torch.equal(res[keep], gt[keep])                  # blended known region is the ground truth, exactly
+
+
+def test_script_ddim_step_bit_exact(cuda_lib):
+    """K4's FIDM_SAMPLER_DDIM_SCRIPT mode against the oracle restatement on one strided step."""
+    import fidm_b200 as F
+    from fidm_b200 import _lib as L
+    from fidm_b200.script_sampler import create_ddim_timestep_sequence, script_ddim_table
+    from oracle import diffusion_oracle as dor
+    from oracle import script_oracle as sor
+    d = F.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="quadratic")
+    tab = dor.Tables(F.get_named_beta_schedule("quadratic", 1000))
+    g = torch.Generator().manual_seed(2)
+    B, H = 2, 16
+    gt = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    masks = (torch.rand(B, 1, H, H, generator=g) > 0.5).float()
+    for eta in (0.0, 0.6):
+        seq = create_ddim_timestep_sequence(1000, 50)
+        table = script_ddim_table(d, seq, eta).to(DEV)
+        for k in (0, 25, len(seq) - 2):
+            x = torch.randn(B, 3, H, H, generator=g)
+            mo = torch.randn(B, 6, H, H, generator=g)
+            z = torch.randn(B, 3, H, H, generator=g)
+            n = torch.randn(B, 3, H, H, generator=g)
+            calls = iter([mo])
+            sub = dor.Tables(tab.betas)
+            # one step of the oracle loop: emulate by running a 1-element sequence with the same alphas
+            a_t = torch.tensor(tab.alphas_cumprod[seq[k]]); a_p = torch.tensor(tab.alphas_cumprod[seq[k + 1]])
+            x0 = torch.clamp((x - torch.sqrt(1 - a_t) * mo[:, :3]) / torch.sqrt(a_t), -1, 1)
+            sigma = eta * torch.sqrt((1 - a_p) / (1 - a_t)) * torch.sqrt(1 - a_t / a_p)
+            img = torch.sqrt(a_p) * x0 + torch.sqrt(1 - a_p - sigma ** 2) * mo[:, :3] + sigma * (z if eta > 0 else torch.zeros_like(z))
+            want = img * masks + (torch.sqrt(a_p) * gt + torch.sqrt(1 - a_p) * n) * (1 - masks)
+            r = d._step(L.STEP_UPDATE_INJECT, x.to(DEV), t=k, t_inject=k, model_out=mo.to(DEV),
+                        z=z.to(DEV) if eta > 0 else None, gt=gt.to(DEV), keep=(1 - masks).to(DEV),
+                        inject_noise=n.to(DEV), script_table=table, want_next=True, want_sample=True)
+            assert torch.equal(r["sample"].cpu(), img), (eta, k)
+            assert torch.equal(r["x_next"].cpu(), want), (eta, k)

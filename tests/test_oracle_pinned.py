@@ -100,3 +100,32 @@ def test_oracle_ddim50_loop_matches_reference(golden_dir):
                               noise_fn=lambda kind, t: seeded_noise(kind, t, shape, seed), trace=trace)
     assert psnr(out, gold["final"]) > 60
     assert psnr(trace[24]["pred_xstart"], gold["pred_xstart_t25"]) > 60
+
+
+def test_oracle_script_loops_match_reference(golden_dir):
+    """The evaluation scripts' strided-DDIM / DDPM loops with post-step injection."""
+    from oracle import script_oracle as sor
+    gold = torch.load(os.path.join(golden_dir, "t64_script_loops.pt"))
+    cfg = CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=1)
+    data = synth_batch(1, 64, seed=4)
+    gt, masks = data["gt"], data["mask"]
+    shape = (1, 3, 64, 64)
+
+    def fn(x, t, gt=None, gt_keep_mask=None):
+        return uor.inpaint_forward(sd, cfg, x, t, gt * gt_keep_mask, 1 - gt_keep_mask)
+
+    g = gold["cos100_ddim10_eta"]
+    assert list(sor.ddim_timestep_sequence(1000, 100))[:3] == [999, 990, 980] and len(sor.ddim_timestep_sequence(1000, 100)) == 101
+    tab = dor.Tables(get_named_beta_schedule(g["sched"], g["steps"]))
+    with torch.no_grad():
+        out = sor.script_ddim_loop(tab, fn, shape, gt, masks, g["n_ddim"], eta=g["eta"],
+                                   x_T=seeded_noise("xT", 0, shape, g["seed_noise"]),
+                                   noise_fn=lambda kind, t: seeded_noise(kind, t, shape, g["seed_noise"]))
+    assert psnr(out, g["final"]) > 60
+    g = gold["cos30_ddpm"]
+    tab = dor.Tables(get_named_beta_schedule(g["sched"], g["steps"]))
+    with torch.no_grad():
+        out = sor.script_ddpm_loop(tab, fn, shape, gt, masks, x_T=seeded_noise("xT", 0, shape, g["seed_noise"]),
+                                   noise_fn=lambda kind, t: seeded_noise(kind, t, shape, g["seed_noise"]))
+    assert psnr(out, g["final"]) > 60
