@@ -43,7 +43,8 @@ class GnArgs(C.Structure):
                 ("groups", i32), ("eps", C.c_float), ("x", vp), ("ld_x", i32),
                 ("gamma", fp), ("beta", fp), ("scale_shift", fp), ("ld_ss", i32),
                 ("silu", i32), ("resample", i32), ("skip_norm", i32), ("y", vp), ("ld_y", i32),
-                ("y_raw", vp), ("ld_raw", i32), ("stats", dp)]
+                ("y_raw", vp), ("ld_raw", i32), ("stats", dp),
+                ("chansum", fp), ("ld_chansum", i32)]
 
 
 class ConvArgs(C.Structure):
@@ -53,7 +54,7 @@ class ConvArgs(C.Structure):
                 ("x2", vp), ("ld_x2", i32), ("cin2", i32), ("w2", vp),
                 ("bias", fp), ("row_add", fp), ("ld_row_add", i32),
                 ("residual", vp), ("ld_res", i32), ("y", vp), ("ld_y", i32),
-                ("y_nchw_f32", i32), ("cout_valid", i32)]
+                ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp)]
 
 
 class AttnArgs(C.Structure):
@@ -74,6 +75,8 @@ SYMBOLS = {
     "fidm_linear_small": (C.c_int, [fp, vp, i32, fp, fp, i32, i32, i32, i32, vp]),
     "fidm_groupnorm_silu_nhwc": (C.c_int, [_P(GnArgs), vp]),
     "fidm_groupnorm_workspace_bytes": (C.c_int64, [i32, i32]),
+    "fidm_groupnorm_reduce_colsum": (C.c_int, [fp, i32, i32, i32, fp, i32, i32, vp]),
+    "fidm_conv_colsum_slots": (C.c_int, [i32, i32]),
     "fidm_conv2d_nhwc_bf16": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_conv2d_nhwc_simt": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_attention_qkv_nhwc_bf16": (C.c_int, [_P(AttnArgs), vp]),

@@ -41,6 +41,7 @@ struct ConvTcParams {
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
   float* y_nchw; int cout_valid;   // non-null: fp32 NCHW output of the first cout_valid channels
+  float* colsum; int colsum_slots; int cout;   // optional fused GroupNorm column sums
 };
 
 constexpr int kEpiWarps = 4;
@@ -288,6 +289,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_4d(&tmY, staging + sbuf * kStagingBytes, cbase, w0, h0, n0);
               bulk_commit_group();
             }
+            if (p.colsum) {
+              // Fused GroupNorm statistics: per-channel (sum, sum of squares) of the bf16 tile just staged.
+              // Thread = (column, half of the rows); a warp reads 32 consecutive channels of one row
+              // (conflict-free under the 128-byte swizzle).  Rows 0-63 / 64-127 are separate partial rows
+              // (with TN == 2 they are two different images).
+              const int col = threadIdx.x & 63, half = threadIdx.x >> 6;
+              const uint8_t* sb0 = staging + sbuf * kStagingBytes + (col & 7) * 2;
+              const int unit = col >> 3;
+              float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 8
+              for (int r = half * 64; r < half * 64 + 64; ++r) {
+                const uint16_t raw = *reinterpret_cast<const uint16_t*>(sb0 + r * 128 + ((unit ^ (r & 7)) << 4));
+                const float v = __uint_as_float((uint32_t)raw << 16);
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+              const int img = n0 + (p.TN == 2 ? half : 0);
+              if (img < p.B && m_blk < m_tiles) {
+                const int slot = (p.TN == 1) ? ((m_blk % (p.tiles_w * p.tiles_h)) * 2 + half) : 0;
+                float2* dst = reinterpret_cast<float2*>(p.colsum) +
+                              ((long long)img * p.colsum_slots + slot) * p.cout + cbase + col;
+                *dst = make_float2(s1, s2);
+              }
+            }
             sbuf ^= 1;
           }
         }
@@ -410,6 +435,9 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr;
   p.cout_valid = a.cout_valid;
+  p.colsum = a.colsum; p.cout = a.cout;
+  p.colsum_slots = (p.TN == 1) ? p.tiles_w * p.tiles_h * 2 : 1;
+  if (a.colsum) FIDM_REQUIRE(!a.y_nchw_f32 && p.TN <= 2 && BLOCK_N >= 64, FIDM_E_SHAPE, "conv_tc: colsum not supported for this shape");
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
   int rc;
@@ -455,6 +483,14 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
 }
 
 }  // namespace fidm
+
+extern "C" int fidm_conv_colsum_slots(int32_t height, int32_t width) {
+  int tw, th, tn;
+  fidm::pick_pixel_box(width, height, &tw, &th, &tn);
+  if (tn == 1) return (width / tw) * (height / th) * 2;
+  if (tn == 2) return 1;
+  return 0;
+}
 
 extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
   using namespace fidm;

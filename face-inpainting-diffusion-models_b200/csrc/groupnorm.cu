@@ -118,6 +118,51 @@ __global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials,
   }
 }
 
+// Small tensors (L2-resident): one block per (image, group) reads that group's channel slice of every pixel
+// and reduces it in a fixed tree -- no workspace, no cross-block step, one short launch.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) gn_stats_direct_kernel(const GnParams p) {
+  const fidm_gn_args& a = p.a;
+  __shared__ double red[8][2];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int hw = a.height * a.width;
+  const int cpg = a.channels / a.groups;
+  const int vpp = cpg / VEC;                          // vectors per pixel in this group
+  const T* base = reinterpret_cast<const T*>(a.x) + (long long)n * hw * a.ld_x + g * cpg;
+  float s = 0.0f, ss = 0.0f;
+  const int total = hw * vpp;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int px = i / vpp, j = i - px * vpp;
+    float f[VEC];
+    load_vec<T, VEC>(base + (long long)px * a.ld_x + j * VEC, f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      s += f[k];
+      ss = fmaf(f[k], f[k], ss);
+    }
+  }
+  double ds = (double)s, dss = (double)ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ds; red[threadIdx.x >> 5][1] = dss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0 += red[k][0]; a1 += red[k][1]; }
+    const double cnt = (double)cpg * hw;
+    const double mean = a0 / cnt;
+    double var = a1 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* mr = reinterpret_cast<float*>(a.stats) + ((long long)n * a.groups + g) * 2;
+    mr[0] = (float)mean;
+    mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+}
+
 template <bool FAST>
 __device__ __forceinline__ float silu_f(float v) {
   if (FAST) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx) instead of ex2 + rcp
@@ -130,7 +175,7 @@ __device__ __forceinline__ float silu_f(float v) {
 }
 
 template <typename T, typename TY, int VEC, int RESAMPLE>
-__global__ void gn_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnParams p) {
   const fidm_gn_args& a = p.a;
   constexpr bool FAST = (sizeof(T) == 2);
   const int n = blockIdx.y;
@@ -147,8 +192,36 @@ __global__ void gn_apply_kernel(const GnParams p) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { A[i] = 1.0f; B[i] = 0.0f; }
   } else {
-    const float* mr = reinterpret_cast<const float*>(a.stats) + ((long long)n * a.groups + g) * 2;
-    const float meanf = mr[0], rstd = mr[1];
+    float meanf, rstd;
+    if (a.chansum) {
+      // statistics from the producer conv's fused column sums: the block stages the image's channel sums in
+      // shared memory (one coalesced read), `groups` threads fold their channels in a fixed order.
+      extern __shared__ float2 cs_s[];                   // [channels] then [groups] (mean, rstd)
+      float2* mr_s = cs_s + a.channels;
+      const float2* cs = reinterpret_cast<const float2*>(a.chansum) + (long long)n * a.ld_chansum;
+      for (int c = threadIdx.x; c < a.channels; c += blockDim.x) cs_s[c] = cs[c];
+      __syncthreads();
+      if (threadIdx.x < a.groups) {
+        double ds = 0.0, dss = 0.0;
+        for (int k = 0; k < cpg; ++k) {
+          const float2 v = cs_s[threadIdx.x * cpg + k];
+          ds += (double)v.x;
+          dss += (double)v.y;
+        }
+        const double cnt = (double)cpg * hw;
+        const double mean = ds / cnt;
+        double var = dss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr_s[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+      }
+      __syncthreads();
+      meanf = mr_s[g].x;
+      rstd = mr_s[g].y;
+    } else {
+      const float* mr = reinterpret_cast<const float*>(a.stats) + ((long long)n * a.groups + g) * 2;
+      meanf = mr[0];
+      rstd = mr[1];
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float ga = a.gamma ? a.gamma[c0 + i] : 1.0f;
@@ -171,15 +244,29 @@ __global__ void gn_apply_kernel(const GnParams p) {
 
   if (RESAMPLE == FIDM_RESAMPLE_NONE) {
     const int p0 = blockIdx.x * p.pix_per_blk, p1 = min(hw, p0 + p.pix_per_blk);
-    for (int px = p0 + pl; px < p1; px += p.ppi) {
-      float f[VEC];
-      load_vec<T, VEC>(xin + (long long)px * a.ld_x, f);
+    // 4 independent 16-byte loads in flight per thread (kept packed to stay within 64 registers): with one
+    // load per thread the kernel is latency-bound at ~70 % of the HBM copy rate (Little's law).
+    constexpr int U = 4;
+    for (int px = p0 + pl; px < p1; px += p.ppi * U) {
+      Vec<T, VEC> raw[U];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float y = fmaf(f[i], A[i], B[i]);
-        f[i] = a.silu ? silu_f<FAST>(y) : y;
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * p.ppi;
+        if (q < p1) raw[u] = *reinterpret_cast<const Vec<T, VEC>*>(xin + (long long)q * a.ld_x);
       }
-      store_vec<TY, VEC>(yo + ((long long)n * hw + px) * a.ld_y + c0, f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * p.ppi;
+        if (q < p1) {
+          float f[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float y = fmaf(to_f32<T>(raw[u].v[i]), A[i], B[i]);
+            f[i] = a.silu ? silu_f<FAST>(y) : y;
+          }
+          store_vec<TY, VEC>(yo + ((long long)n * hw + q) * a.ld_y + c0, f);
+        }
+      }
     }
   } else if (RESAMPLE == FIDM_RESAMPLE_DOWN) {
     const int Ho = H / 2, Wo = W / 2, ohw = Ho * Wo;
@@ -251,7 +338,10 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
     return (npix + p.pix_per_blk - 1) / p.pix_per_blk;
   };
   int chunks;
-  if (!a.skip_norm) {
+  if (!a.skip_norm && !a.chansum && (long long)hw * (a.channels / a.groups) <= 64 * 64 * 64) {
+    gn_stats_direct_kernel<T, VEC><<<dim3(a.groups, a.batch), 256, 0, st>>>(p);
+    FIDM_CHECK_LAUNCH("groupnorm stats (direct)");
+  } else if (!a.skip_norm && !a.chansum) {
     // workspace: [batch*groups*2] floats (mean, rstd) padded to doubles, then the per-block partials
     double* partials = a.stats + (long long)a.batch * a.groups;
     chunks = plan(hw);
@@ -268,12 +358,13 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
   }
   chunks = plan(it_hw);
   dim3 grid(chunks, a.batch);
+  const size_t sm = a.chansum ? sizeof(float2) * (a.channels + a.groups) : 0;
   if (a.resample == FIDM_RESAMPLE_NONE)
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_NONE><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_NONE><<<grid, threads, sm, st>>>(p);
   else if (a.resample == FIDM_RESAMPLE_DOWN)
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_DOWN><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_DOWN><<<grid, threads, sm, st>>>(p);
   else
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_UP><<<grid, threads, 0, st>>>(p);
+    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_UP><<<grid, threads, sm, st>>>(p);
   FIDM_CHECK_LAUNCH("groupnorm apply");
   return 0;
 }
@@ -299,7 +390,7 @@ static int dispatch_vec(const fidm_gn_args& a, cudaStream_t st) {
 
 extern "C" int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream) {
   using namespace fidm;
-  FIDM_REQUIRE(a && a->x && a->y && (a->stats || a->skip_norm), FIDM_E_BADARG, "groupnorm: null x/y/stats");
+  FIDM_REQUIRE(a && a->x && a->y && (a->stats || a->skip_norm || a->chansum), FIDM_E_BADARG, "groupnorm: null x/y/stats");
   FIDM_REQUIRE(a->batch > 0 && a->height > 0 && a->width > 0 && a->channels > 0, FIDM_E_BADARG, "groupnorm: empty shape");
   FIDM_REQUIRE(a->groups > 0 && a->groups <= 64 && a->channels % a->groups == 0, FIDM_E_SHAPE,
                "groupnorm: channels %d not divisible into %d groups", a->channels, a->groups);
@@ -313,6 +404,54 @@ extern "C" int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t str
   if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(*a, (cudaStream_t)stream);
   if (a->dtype == FIDM_F32) return dispatch_vec<float, float>(*a, (cudaStream_t)stream);
   FIDM_REQUIRE(false, FIDM_E_BADARG, "groupnorm: bad dtype %d", a->dtype);
+}
+
+namespace fidm {
+// chansum[n][c0+c] = sum_{slot} colsum[n][slot][c]   (double accumulation, fixed order)
+constexpr int RS = 32;   // slices of the slot range per block (fixed summation tree: slice, then slices in order)
+__global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2* __restrict__ colsum, int slots, int C,
+                                                                   float2* __restrict__ chansum, int ld, int c0) {
+  __shared__ double red[RS][32][2];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int j = threadIdx.x >> 5;
+  double ds = 0.0, dss = 0.0;
+  if (c < C) {
+    const float2* q = colsum + (long long)n * slots * C + c;
+    int s = j;
+    for (; s + 3 * RS < slots; s += 4 * RS) {
+      const float2 v0 = __ldcg(q + (long long)s * C), v1 = __ldcg(q + (long long)(s + RS) * C);
+      const float2 v2 = __ldcg(q + (long long)(s + 2 * RS) * C), v3 = __ldcg(q + (long long)(s + 3 * RS) * C);
+      ds += (double)v0.x; dss += (double)v0.y; ds += (double)v1.x; dss += (double)v1.y;
+      ds += (double)v2.x; dss += (double)v2.y; ds += (double)v3.x; dss += (double)v3.y;
+    }
+    for (; s < slots; s += RS) {
+      const float2 v = __ldcg(q + (long long)s * C);
+      ds += (double)v.x; dss += (double)v.y;
+    }
+  }
+  red[j][threadIdx.x & 31][0] = ds;
+  red[j][threadIdx.x & 31][1] = dss;
+  __syncthreads();
+  if (j == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < RS; ++k) { a += red[k][threadIdx.x][0]; b += red[k][threadIdx.x][1]; }
+    chansum[(long long)n * ld + c0 + c] = make_float2((float)a, (float)b);
+  }
+}
+}  // namespace fidm
+
+extern "C" int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, int32_t slots, int32_t channels,
+                                            float* chansum, int32_t ld_chansum, int32_t c0, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(colsum && chansum && batch > 0 && slots > 0 && channels > 0 && c0 >= 0 && c0 + channels <= ld_chansum,
+               FIDM_E_BADARG, "reduce_colsum: bad args");
+  dim3 grid((channels + 31) / 32, batch);
+  gn_reduce_colsum_kernel<<<grid, 32 * RS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(colsum), slots, channels,
+                                                                 reinterpret_cast<float2*>(chansum), ld_chansum, c0);
+  FIDM_CHECK_LAUNCH("reduce_colsum");
+  return 0;
 }
 
 extern "C" int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups) {

@@ -176,6 +176,11 @@ class Plan:
         self.ops = []
         self.pool = _Pool(dev, dt)
         self.keep = []
+        # fused GroupNorm statistics: per-storage [B, ld, 2] channel sums written by the producing convs
+        self.fuse_stats = os.environ.get("FIDM_FUSE_GN_STATS", "1") != "0" and weights.precision == "bf16"
+        self.chansum = {}        # id(storage) -> fp32 [B, ld, 2]
+        self.coverage = {}       # id(storage) -> [(c0, channels)]
+        self.colsum_scratch = {}  # numel -> fp32 scratch for the per-tile partial rows
         cfg = topo.cfg
         mc, ted = cfg["model_channels"], topo.time_embed_dim
         self.ssn = cfg["use_scale_shift_norm"]
@@ -251,7 +256,18 @@ class Plan:
         self.ops.append((fn, args))
 
     def _new(self, H, W, Cn, dtype=None):
-        return Ref(self.pool.get(self.B, H, W, Cn, dtype), 0, Cn, H, W)
+        t = self.pool.get(self.B, H, W, Cn, dtype)
+        self.coverage.pop(id(t), None)           # new contents: previously fused statistics are stale
+        return Ref(t, 0, Cn, H, W)
+
+    def _covered(self, x):
+        """True if fused channel sums exist for every channel of the view `x`."""
+        rng = sorted(self.coverage.get(id(x.storage), []))
+        pos = x.c0
+        for c0, n in rng:
+            if c0 <= pos < c0 + n:
+                pos = c0 + n
+        return pos >= x.c0 + x.channels
 
     def _wdtype(self, name):
         """dtype of the weights of conv `name` == dtype its (normalized) input operand must have."""
@@ -278,11 +294,14 @@ class Plan:
         if y_raw is not None:
             a.y_raw, a.ld_raw = y_raw.ptr, y_raw.ld
         a.stats = L.ptr(self.stats)
+        if not skip_norm and self._covered(x):
+            cs = self.chansum[id(x.storage)]
+            a.chansum, a.ld_chansum = L.ptr(cs, x.c0 * 8), cs.shape[1]
         self.keep.append(a)
         self._op(self.lib.fidm_groupnorm_silu_nhwc, C.byref(a))
 
     def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
-              cout_valid=None):
+              cout_valid=None, stats=True):
         w = self.w
         wt, bias, cin_pad, cout_pad, ks = w.conv[name]
         assert x.channels == cin_pad, (name, x.channels, cin_pad)
@@ -310,7 +329,30 @@ class Plan:
                  (x2 is None or x2.channels % 64 == 0))
         assert tc_ok or wt.dtype != torch.float16
         fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
+        # Fusing the consumer GroupNorm's statistics into this epilogue pays off where the separate statistics
+        # pass is HBM-bound (large tensors) and the epilogue is off the critical path (long K loop); measured
+        # on B200: 128^2 and larger, K >= 1152.  Small tensors keep the (L2-resident) statistics kernel.
+        k_total = ks * ks * cin_pad + (x2.channels if x2 is not None else 0)
+        slots = self.lib.fidm_conv_colsum_slots(x.H, x.W) if (
+            tc_ok and nchw_out is None and stats and self.fuse_stats and cout_pad % 64 == 0 and
+            x.H * x.W >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
+        if slots > 0:
+            n = self.B * slots * cout_pad * 2
+            if n not in self.colsum_scratch:
+                self.colsum_scratch[n] = torch.empty(n, device=w.device, dtype=torch.float32)
+            a.colsum = L.ptr(self.colsum_scratch[n])
         self._op(fn, C.byref(a))
+        if slots > 0:
+            sid = id(y.storage)
+            if sid not in self.chansum:
+                self.chansum[sid] = torch.zeros(self.B, y.ld, 2, device=w.device, dtype=torch.float32)
+            cs = self.chansum[sid]
+            self._op(self.lib.fidm_groupnorm_reduce_colsum, a.colsum, self.B, slots, cout_pad, L.ptr(cs), y.ld, y.c0)
+            self.coverage.setdefault(sid, []).append((y.c0, cout_pad))
+        elif y is not None:
+            # a producer without fused statistics invalidates whatever was recorded for these channels
+            self.coverage[id(y.storage)] = [r for r in self.coverage.get(id(y.storage), [])
+                                            if r[0] + r[1] <= y.c0 or r[0] >= y.c0 + cout_pad]
 
     def _attention(self, qkv, out, heads, head_dim):
         w = self.w
@@ -324,6 +366,7 @@ class Plan:
         self._op(fn, C.byref(a))
 
     TC_ATTENTION = True
+    FUSE_MIN_PIXELS = 128 * 128
 
     # ------------------------------------------------------------------ layers
     def _block(self, blk, x, dst):
@@ -385,7 +428,7 @@ class Plan:
         a = self._new(x.H, x.W, Cn, self._wdtype(n + ".qkv"))
         self._gn(x, a, n + ".norm", silu=False)
         qkv = self._new(x.H, x.W, 3 * Cn)
-        self._conv(n + ".qkv", a, qkv)
+        self._conv(n + ".qkv", a, qkv, stats=False)
         self._release(a)
         o = self._new(x.H, x.W, Cn)
         self._attention(qkv, o, layer.heads, Cn // layer.heads)
@@ -466,7 +509,7 @@ class Plan:
         n = 0
         for fn, args in self.ops:
             if fn is self.lib.fidm_groupnorm_silu_nhwc:
-                n += 1 if args[0]._obj.skip_norm else 2
+                n += 1 if (args[0]._obj.skip_norm or args[0]._obj.chansum) else 2
             else:
                 n += 1
         return n

@@ -76,7 +76,7 @@ def linear_small(x, w, bias=None, silu_input=False):
 
 
 def groupnorm_silu(x, gamma=None, beta=None, *, scale_shift=None, silu=True, resample="none", want_raw=False,
-                   skip_norm=False, out=None, groups=32, eps=1e-5, out_dtype=None):
+                   skip_norm=False, out=None, groups=32, eps=1e-5, out_dtype=None, chansum=None):
     n, h, w, c, ld = _nhwc(x)
     mode = {"none": L.RESAMPLE_NONE, "down": L.RESAMPLE_DOWN, "up": L.RESAMPLE_UP}[resample]
     ho, wo = (h // 2, w // 2) if resample == "down" else ((2 * h, 2 * w) if resample == "up" else (h, w))
@@ -96,12 +96,14 @@ def groupnorm_silu(x, gamma=None, beta=None, *, scale_shift=None, silu=True, res
     if raw is not None:
         a.y_raw, a.ld_raw = L.ptr(raw), c
     a.stats = L.ptr(stats)
+    if chansum is not None:            # [N, ld, 2] fp32 channel sums from conv2d(..., want_chansum=True)
+        a.chansum, a.ld_chansum = L.ptr(chansum), chansum.shape[1]
     L.check(L.lib().fidm_groupnorm_silu_nhwc(C.byref(a), L.stream()), "groupnorm")
     return (y, raw) if want_raw else y
 
 
 def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=None, w2=None, out=None,
-           nchw_out_channels=None, impl="auto"):
+           nchw_out_channels=None, impl="auto", want_chansum=False):
     """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto"."""
     n, h, w, cin, ld = _nhwc(x)
     cout, ks = w_krsc.shape[0], w_krsc.shape[1]
@@ -131,7 +133,18 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
         impl = "tc" if (x.dtype in (torch.bfloat16, torch.float16) and stride == 1 and cin % 64 == 0 and
                         (cout % 64 == 0 or (nchw_out_channels is not None and cout == 16))) else "simt"
     fn = L.lib().fidm_conv2d_nhwc_bf16 if impl == "tc" else L.lib().fidm_conv2d_nhwc_simt
+    colsum = None
+    if want_chansum:
+        slots = L.lib().fidm_conv_colsum_slots(h, w)
+        assert impl == "tc" and slots > 0 and nchw_out_channels is None
+        colsum = torch.empty(n, slots, cout, 2, device=x.device, dtype=torch.float32)
+        a.colsum = L.ptr(colsum)
     L.check(fn(C.byref(a), L.stream()), "conv2d/" + impl)
+    if want_chansum:
+        chansum = torch.zeros(n, cout, 2, device=x.device, dtype=torch.float32)
+        L.check(L.lib().fidm_groupnorm_reduce_colsum(L.ptr(colsum), n, slots, cout, L.ptr(chansum), cout, 0, L.stream()),
+                "reduce_colsum")
+        return y, chansum
     return y
 
 

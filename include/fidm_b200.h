@@ -164,9 +164,14 @@ typedef struct fidm_gn_args {
   void* y; int32_t ld_y;                /* activated output (resampled resolution) */
   void* y_raw; int32_t ld_raw;          /* optional: resample(x) without norm (x_upd, nn.py:194) */
   double* stats;                        /* workspace (unused when skip_norm) */
+  const float* chansum; int32_t ld_chansum;  /* optional [batch][ld_chansum][2] per-channel (sum, sum of squares)
+                                           of x (from fidm_groupnorm_reduce_colsum): replaces the statistics pass */
 } fidm_gn_args;
 int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream);
 int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
+/* chansum[n][c0 + c] = sum over the `slots` partial rows of image n of colsum[n][slot][c]  (fixed order) */
+int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, int32_t slots, int32_t channels,
+                                 float* chansum, int32_t ld_chansum, int32_t c0, fidm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  convolution as implicit GEMM, NHWC activations, KRSC weights ([Cout][kh][kw][Cin]).
@@ -198,7 +203,13 @@ typedef struct fidm_conv_args {
   void* y; int32_t ld_y;
   int32_t y_nchw_f32;                   /* 1: y is fp32 [batch][cout_valid][Ho][Wo] */
   int32_t cout_valid;                   /* channels actually stored (<= cout; head: 6 of 16) */
+  float* colsum;                        /* optional (tensor-core entry, NHWC output, images of >= 64 pixels):
+                                           per-channel partial (sum, sum of squares) of the stored bf16 output,
+                                           [batch][fidm_conv_colsum_slots()][cout][2] fp32 -- the GroupNorm
+                                           statistics pass of the consumer, fused into this epilogue */
 } fidm_conv_args;
+/* number of partial rows per image the tensor-core conv writes into `colsum` (0: not supported for this size) */
+int fidm_conv_colsum_slots(int32_t height, int32_t width);
 int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream);
 int fidm_conv2d_nhwc_simt(const fidm_conv_args* a, fidm_stream_t stream);
 

@@ -138,3 +138,21 @@ def test_conv_tc_fp16_operands(cuda_lib, B, H, W, Cin, Cout, Cin2):
     y = ops.conv2d(x, ops.repack_weight(w.float(), torch.float16), b, residual=res, impl="tc", **kw)
     assert y.dtype == torch.bfloat16
     _check(y, _ref(x, w, b, residual=res, x2=x2, w2=w2), "fp16 operands")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 64, 256), (3, 8, 8, 128, 128), (1, 256, 256, 64, 256),
+                                            (2, 16, 16, 64, 192), (5, 32, 32, 64, 64)])
+def test_conv_tc_fused_groupnorm_statistics(cuda_lib, B, H, W, Cin, Cout):
+    """The conv epilogue's per-channel sums == sums of the stored bf16 output, and GroupNorm driven by them
+    == GroupNorm with its own statistics pass."""
+    from fidm_b200 import ops
+    x, w, b, g = _mk(B, H, W, Cin, Cout, 3, seed=H + Cout)
+    y, cs = ops.conv2d(x, ops.repack_weight(w.float()), b, impl="tc", want_chansum=True)
+    yf = y.float()
+    want = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1)
+    assert torch.allclose(cs, want, rtol=2e-4, atol=2e-2)
+    gamma = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    a = ops.groupnorm_silu(y, gamma, beta, silu=True, out_dtype=torch.float16, chansum=cs)
+    r = ops.groupnorm_silu(y, gamma, beta, silu=True, out_dtype=torch.float16)
+    assert torch.allclose(a.float(), r.float(), atol=2e-3, rtol=2e-3)
