@@ -54,7 +54,8 @@ class ConvArgs(C.Structure):
                 ("x2", vp), ("ld_x2", i32), ("cin2", i32), ("w2", vp),
                 ("bias", fp), ("row_add", fp), ("ld_row_add", i32),
                 ("residual", vp), ("ld_res", i32), ("y", vp), ("ld_y", i32),
-                ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp)]
+                ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp),
+                ("splitk_ws", vp), ("splitk_ws_bytes", C.c_int64)]
 
 
 class AttnArgs(C.Structure):

@@ -42,9 +42,12 @@ struct ConvTcParams {
   const __nv_bfloat16* residual; int ld_res;
   float* y_nchw; int cout_valid;   // non-null: fp32 NCHW output of the first cout_valid channels
   float* colsum; int colsum_slots; int cout;   // optional fused GroupNorm column sums
+  int split_k;             // >1: the K loop of every tile is split over split_k CTAs (low-resolution layers)
+  float* sk_ws; int* sk_cnt;   // fp32 partial tiles [tile][split][BLOCK_N][128], per-tile arrival counters
 };
 
 constexpr int kEpiWarps = 4;
+constexpr long long kSplitCounterBytes = 65536;
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;                 // 128 rows x 64 bf16
 constexpr int kStagingBytes = 128 * 128;           // one 128 x 64 bf16 output chunk
@@ -77,6 +80,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  volatile uint32_t* sk_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // rank 0 = leader (issues the MMAs)
@@ -87,7 +91,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // CG = 2: work items are PAIRS of consecutive M tiles (a phantom tile past the end is zero-filled by
   // TMA and clipped on store)
-  const int total_tiles = ((m_tiles + CG - 1) / CG) * p.n_blocks;
+  const int S = p.split_k;
+  const int total_tiles = ((m_tiles + CG - 1) / CG) * p.n_blocks * S;     // work units = (tile, K split)
   const int pad = p.ksize >> 1;
 
   if (warp == 4 && lane == 0) {
@@ -115,13 +120,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
+      for (int wu = unit; wu < total_tiles; wu += n_units) {
+        const int tile = wu / S, split = wu - tile * S;
+        const int it0 = (int)((long long)split * k_iters / S), it1 = (int)((long long)(split + 1) * k_iters / S);
         const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
         const int w0 = (m_blk % p.tiles_w) * p.TW;
         const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
         const int co0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;   // this CTA's share of the weight tile
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -165,11 +172,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int main_iters = p.ksize * p.ksize * p.kc1;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
+      for (int wu = unit; wu < total_tiles; wu += n_units) {
+        const int split = wu % S;
+        const int it0 = (int)((long long)split * k_iters / S), it1 = (int)((long long)(split + 1) * k_iters / S);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -178,8 +187,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t idesc = it < main_iters ? idesc_main : idesc_bf16;
 #pragma unroll
           for (int k = 0; k < 4; ++k) { // 4 x (K = 16 elements = 32 B) inside the 128-byte swizzle atom
-            if (CG == 1) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
-            else umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+            const uint32_t accum = (it > it0 || k > 0) ? 1u : 0u;
+            if (CG == 1) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+            else umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_2sm(&empty_bar[stage], 3);
@@ -198,7 +208,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (threadIdx.x == 0);
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0;
-    for (int tile = unit; tile < total_tiles; tile += n_units) {
+    for (int wu = unit; wu < total_tiles; wu += n_units) {
+      const int tile = wu / S, split = wu - tile * S;
       const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
       const int w0 = (m_blk % p.tiles_w) * p.TW;
       const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
@@ -213,8 +224,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
 
       if constexpr (BLOCK_N >= 64) {
+        bool finish = true;
+        if (S > 1) {
+          // ---- split-K: park this CTA's fp32 partial tile ([column][row]: coalesced), then the LAST CTA of the
+          // tile to arrive folds the S partials in split order (deterministic) and runs the epilogue.
+          float* wsp = p.sk_ws + ((long long)tile * S + split) * (BLOCK_N * 128) + row;
+#pragma unroll 1
+          for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(t_acc + ch * 64, v0);
+            tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              __stcg(wsp + (ch * 64 + j) * 128, __uint_as_float(v0[j]));
+              __stcg(wsp + (ch * 64 + 32 + j) * 128, __uint_as_float(v1[j]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          __threadfence();
+          named_bar_sync(1, kEpiWarps * 32);
+          if (issuer) {
+            const int prev = atomicAdd(p.sk_cnt + tile, 1);
+            const bool last = (prev == S - 1);
+            if (last) p.sk_cnt[tile] = 0;            // re-arm for the next launch
+            *sk_flag = last ? 1u : 0u;
+          }
+          named_bar_sync(2, kEpiWarps * 32);
+          finish = (*sk_flag != 0u);
+          if (finish) __threadfence();
+        }
+        if (finish) {
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+          const int cbase = co0 + ch * 64;
+          float f[64];
+          if (S > 1) {
+            const float* rp = p.sk_ws + (long long)tile * S * (BLOCK_N * 128) + (ch * 64) * 128 + row;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] = __ldcg(rp + j * 128);
+            for (int sp = 1; sp < S; ++sp) {
+              rp += BLOCK_N * 128;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) f[j] += __ldcg(rp + j * 128);
+            }
+          } else {
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(t_acc + ch * 64, v0);
           tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
@@ -224,10 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) { if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0); }
           }
-          const int cbase = co0 + ch * 64;
-          float f[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+          }
           if (p.bias) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
 #pragma unroll
@@ -316,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sbuf ^= 1;
           }
         }
+        }  // if (finish)
       } else {
         // BLOCK_N == 16: narrow head (out.2, 6 of 16 channels), fp32 NCHW output only
         uint32_t v[16];
@@ -419,9 +475,10 @@ int pick_pixel_box(int W, int H, int* tw, int* th, int* tn) {
 }
 
 template <int BLOCK_N, int CG>
-static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
+static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k = 1) {
   using Cfg = ConvCfg<BLOCK_N, CG>;
   ConvTcParams p;
+  p.split_k = split_k; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   p.B = a.batch; p.H = a.height; p.W = a.width;
   pick_pixel_box(a.width, a.height, &p.TW, &p.TH, &p.TN);
   FIDM_REQUIRE(p.TN <= 256, FIDM_E_SHAPE, "conv_tc: image %dx%d too small for a 128-pixel tile", a.height, a.width);
@@ -460,7 +517,18 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st) {
     attr_set = true;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int units = ((m_tiles + CG - 1) / CG) * p.n_blocks;          // tiles (CG=1) or tile pairs (CG=2)
+  if (split_k > 1) {
+    // workspace: the first kSplitCounterBytes hold one int arrival counter per tile (zero on entry and on exit --
+    // a FIXED region, so that partial tiles of one launch can never be read as counters by the next), then
+    // [tiles * split_k] fp32 partial tiles.
+    const long long tiles = (long long)m_tiles * p.n_blocks;
+    const long long need = kSplitCounterBytes + tiles * split_k * BLOCK_N * 128 * 4;
+    FIDM_REQUIRE(CG == 1 && BLOCK_N >= 64 && a.splitk_ws && a.splitk_ws_bytes >= need && tiles * 4 <= kSplitCounterBytes,
+                 FIDM_E_BADARG, "conv_tc: split-K workspace too small (%lld needed)", need);
+    p.sk_cnt = reinterpret_cast<int*>(a.splitk_ws);
+    p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a.splitk_ws) + kSplitCounterBytes);
+  }
+  const int units = ((m_tiles + CG - 1) / CG) * p.n_blocks * split_k;  // (tile | tile pair) x K split
   const int slots = num_sms() / CG;
   const int grid = (units < slots ? units : slots) * CG;
   if (CG == 1) {
@@ -520,6 +588,33 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   static const bool pair_ok = getenv("FIDM_CONV_CTA_PAIR") == nullptr || atoi(getenv("FIDM_CONV_CTA_PAIR")) != 0;
   if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want)
     return pair_ok ? launch_conv_tc<256, 2>(*a, st) : launch_conv_tc<256, 1>(*a, st);
-  if (a->cout % 128 == 0 && m_tiles * (a->cout / 128) >= want) return launch_conv_tc<128, 1>(*a, st);
-  return launch_conv_tc<64, 1>(*a, st);
+  // Low-resolution layers (few pixel tiles, deep K).  Candidate (N tile, K split) pairs are scored with a small
+  // cost model in SM cycles: tensor time of one CTA's share, L2->SM operand traffic of the whole grid against the
+  // ~12 KB/clk the L2 delivers (measured: 442 MB in 62 us on the 16x16 layers) (these layers re-read the weights once per pixel tile), and the fixed-order
+  // fold of the split partials by the last CTA of each tile.
+  const int k_iters = a->ksize * a->ksize * (a->cin / 64) + (a->x2 ? a->cin2 / 64 : 0);
+  static const bool split_ok = getenv("FIDM_CONV_SPLIT_K") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_K")) != 0;
+  int best_n = 0, best_s = 1;
+  double best = 1e30;
+  const int ns[3] = {256, 128, 64};
+  const double mma_cyc[3] = {128.0, 72.0, 48.0};
+  const int sms = num_sms();
+  for (int i = 0; i < 3; ++i) {
+    const int N = ns[i];
+    if (a->cout % N) continue;
+    const long long tiles = m_tiles * (a->cout / N);
+    for (int S = 1; S <= 8; ++S) {
+      if (S > 1 && (!split_ok || !a->splitk_ws || k_iters / S < 6)) break;
+      if (S > 1 && (a->splitk_ws_bytes < kSplitCounterBytes + tiles * S * N * 128 * 4 || tiles * 4 > kSplitCounterBytes)) break;
+      const double waves = (double)((tiles * S + sms - 1) / sms);
+      const double compute = waves * ((double)k_iters / S) * 4.0 * mma_cyc[i];
+      const double traffic = (double)tiles * k_iters * (16384.0 + N * 128.0) / 12000.0;
+      const double fold = S > 1 ? (double)S * (N / 64) * 900.0 : 0.0;
+      const double cost = (compute > traffic ? compute : traffic) + fold + 3000.0;
+      if (cost < best) { best = cost; best_n = N; best_s = S; }
+    }
+  }
+  if (best_n == 256) return launch_conv_tc<256, 1>(*a, st, best_s);
+  if (best_n == 128) return launch_conv_tc<128, 1>(*a, st, best_s);
+  return launch_conv_tc<64, 1>(*a, st, best_s);
 }

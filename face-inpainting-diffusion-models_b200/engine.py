@@ -181,6 +181,7 @@ class Plan:
         self.chansum = {}        # id(storage) -> fp32 [B, ld, 2]
         self.coverage = {}       # id(storage) -> [(c0, channels)]
         self.colsum_scratch = {}  # numel -> fp32 scratch for the per-tile partial rows
+        self.splitk_ws = torch.zeros(32 << 20, device=dev, dtype=torch.uint8)   # zero-initialised, kernels re-arm it
         cfg = topo.cfg
         mc, ted = cfg["model_channels"], topo.time_embed_dim
         self.ssn = cfg["use_scale_shift_norm"]
@@ -324,6 +325,7 @@ class Plan:
         else:
             a.y, a.ld_y = y.ptr, y.ld
         a.cout_valid = cout_valid or cout_pad
+        a.splitk_ws, a.splitk_ws_bytes = L.ptr(self.splitk_ws), self.splitk_ws.numel()
         self.keep.append(a)
         tc_ok = (w.precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
                  (x2 is None or x2.channels % 64 == 0))

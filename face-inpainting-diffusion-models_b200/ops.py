@@ -12,6 +12,9 @@ import torch
 from . import _lib as L
 
 
+_SPLITK_WS = None
+
+
 def _nhwc(t):
     assert t.dim() == 4 and t.stride(3) == 1, "NHWC tensor with contiguous channels expected"
     n, h, w, c = t.shape
@@ -133,6 +136,11 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
         impl = "tc" if (x.dtype in (torch.bfloat16, torch.float16) and stride == 1 and cin % 64 == 0 and
                         (cout % 64 == 0 or (nchw_out_channels is not None and cout == 16))) else "simt"
     fn = L.lib().fidm_conv2d_nhwc_bf16 if impl == "tc" else L.lib().fidm_conv2d_nhwc_simt
+    if impl == "tc":
+        global _SPLITK_WS
+        if _SPLITK_WS is None or _SPLITK_WS.device != x.device:
+            _SPLITK_WS = torch.zeros(32 << 20, device=x.device, dtype=torch.uint8)
+        a.splitk_ws, a.splitk_ws_bytes = L.ptr(_SPLITK_WS), _SPLITK_WS.numel()
     colsum = None
     if want_chansum:
         slots = L.lib().fidm_conv_colsum_slots(h, w)

@@ -207,6 +207,9 @@ typedef struct fidm_conv_args {
                                            per-channel partial (sum, sum of squares) of the stored bf16 output,
                                            [batch][fidm_conv_colsum_slots()][cout][2] fp32 -- the GroupNorm
                                            statistics pass of the consumer, fused into this epilogue */
+  void* splitk_ws; int64_t splitk_ws_bytes;  /* optional zero-initialised workspace: lets the tensor-core entry split
+                                           the K loop of low-resolution layers over several CTAs (fixed-order fold,
+                                           counters are left at zero).  32 MB covers every layer of the UNets here. */
 } fidm_conv_args;
 /* number of partial rows per image the tensor-core conv writes into `colsum` (0: not supported for this size) */
 int fidm_conv_colsum_slots(int32_t height, int32_t width);

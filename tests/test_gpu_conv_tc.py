@@ -156,3 +156,23 @@ def test_conv_tc_fused_groupnorm_statistics(cuda_lib, B, H, W, Cin, Cout):
     a = ops.groupnorm_silu(y, gamma, beta, silu=True, out_dtype=torch.float16, chansum=cs)
     r = ops.groupnorm_silu(y, gamma, beta, silu=True, out_dtype=torch.float16)
     assert torch.allclose(a.float(), r.float(), atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,Cin2", [(8, 8, 8, 1024, 1024, 0), (8, 8, 8, 2048, 1024, 2048), (2, 16, 16, 512, 512, 0),
+                                                 (1, 8, 8, 1024, 3072, 0), (8, 16, 16, 1024, 1024, 0)])
+def test_conv_tc_split_k_layers(cuda_lib, B, H, W, Cin, Cout, Cin2):
+    """Low-resolution layers take the split-K path (fixed-order fold): correct, bit-reproducible, and the
+    workspace counters re-arm themselves (back-to-back launches)."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x, w, b, g = _mk(B, H, W, Cin, Cout, 3, seed=Cin + H)
+    wk = ops.repack_weight(w.float())
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g).bfloat16()
+    kw, x2, w2 = {}, None, None
+    if Cin2:
+        x2 = torch.randn(B, H, W, Cin2, device="cuda", generator=g).bfloat16()
+        w2 = (torch.randn(Cout, Cin2, 1, 1, device="cuda", generator=g) / math.sqrt(Cin2)).bfloat16()
+        kw = dict(x2=x2, w2=ops.repack_weight(w2.float()))
+    outs = [ops.conv2d(x, wk, b, residual=res, impl="tc", **kw).clone() for _ in range(3)]
+    _check(outs[0], _ref(x, w, b, residual=res, x2=x2, w2=w2), "split-K")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
