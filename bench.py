@@ -320,7 +320,12 @@ def dominant_kernel_roofline(ops, dev, pk, B):
     return {"kernel": "conv_tc_kernel<256> (3x3, 256->256, 256x256, batch %d)" % B, "bound": "tensor",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_src": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": ms,
-            "flops_per_launch": flops, "traffic": None}
+            "flops_per_launch": flops,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at batch 8 from the committed
+            # `ncu --set full` capture (profiles/r1_ncu_full_conv_gn.txt): 269.7 MB + 247.5 MB; the algorithmic
+            # minimum is 268.4 MB in + 268.4 MB out + 1.2 MB of weights
+            "traffic": 517.1e6 * B / 8, "traffic_src": "profiles/r1_ncu_full_conv_gn.txt",
+            "tensor_pipe_active_pct_ncu": 68.2}
 
 
 if __name__ == "__main__":

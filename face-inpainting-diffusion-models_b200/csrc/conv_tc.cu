@@ -46,9 +46,9 @@ struct ConvTcParams {
   float* sk_ws; int* sk_cnt;   // fp32 partial tiles [tile][split][BLOCK_N][128], per-tile arrival counters
 };
 
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;            // two warpgroups: chunk ch of a tile is drained by warpgroup (ch & 1)
 constexpr long long kSplitCounterBytes = 65536;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // 8 epilogue warps, warp 8 = TMA producer, warp 9 = MMA issuer
 constexpr int kABytes = 128 * 128;                 // 128 rows x 64 bf16
 constexpr int kStagingBytes = 128 * 128;           // one 128 x 64 bf16 output chunk
 
@@ -95,13 +95,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_tiles = ((m_tiles + CG - 1) / CG) * p.n_blocks * S;     // work units = (tile, K split)
   const int pad = p.ksize >> 1;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     if (!p.y_nchw) tma_prefetch_desc(&tmY);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * kEpiWarps); }
@@ -116,7 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -163,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================================================================== MMA issuer
     if (lane == 0 && cta_rank == 0) {
       // second-source (raw residual stream) operands are always bf16
@@ -201,13 +201,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 0-3)
-    const int row = warp * 32 + lane;                 // TMEM lane == pixel row of the tile
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    // ===================================================================== epilogue (warps 0-7)
+    // The epilogue paces the kernel when it is slower than the MMAs of one tile (18.4k cycles for K = 2304), so
+    // two warpgroups drain the accumulator concurrently: warpgroup wg owns the 64-column chunks with (ch & 1) == wg,
+    // its own staging tile, its own named barriers and its own TMA-store issuer.
+    const int wg = warp >> 2, qw = warp & 3;          // warp (qw) may only touch TMEM lanes [32 qw, 32 qw + 32)
+    const int row = qw * 32 + lane;                   // TMEM lane == pixel row of the tile
+    const int etid = row;                             // thread index within the warpgroup
+    const uint32_t lane_sel = (uint32_t)(qw * 32) << 16;
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
-    const bool issuer = (threadIdx.x == 0);
+    const bool issuer = (etid == 0);
+    const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
+    uint8_t* const stage_out = staging + wg * kStagingBytes;
     int acc = 0; uint32_t acc_phase = 0;
-    int sbuf = 0;
     for (int wu = unit; wu < total_tiles; wu += n_units) {
       const int tile = wu / S, split = wu - tile * S;
       const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
@@ -230,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // tile to arrive folds the S partials in split order (deterministic) and runs the epilogue.
           float* wsp = p.sk_ws + ((long long)tile * S + split) * (BLOCK_N * 128) + row;
 #pragma unroll 1
-          for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+          for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
             uint32_t v0[32], v1[32];
             tmem_ld_32x32(t_acc + ch * 64, v0);
             tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
@@ -245,20 +251,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           __threadfence();
-          named_bar_sync(1, kEpiWarps * 32);
-          if (issuer) {
+          named_bar_sync(5, kEpiWarps * 32);
+          if (threadIdx.x == 0) {
             const int prev = atomicAdd(p.sk_cnt + tile, 1);
             const bool last = (prev == S - 1);
             if (last) p.sk_cnt[tile] = 0;            // re-arm for the next launch
             *sk_flag = last ? 1u : 0u;
           }
-          named_bar_sync(2, kEpiWarps * 32);
+          named_bar_sync(6, kEpiWarps * 32);
           finish = (*sk_flag != 0u);
           if (finish) __threadfence();
         }
         if (finish) {
+        if (S == 1 && wg >= BLOCK_N / 64) {           // narrow tile: this warpgroup has no chunk, only releases TMEM
+          __syncwarp();
+          if (lane == 0) { if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0); }
+        }
 #pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+        for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
           const int cbase = co0 + ch * 64;
           float f[64];
           if (S > 1) {
@@ -275,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_32x32(t_acc + ch * 64, v0);
           tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
           tc_wait_ld();
-          if (ch == BLOCK_N / 64 - 1) {       // all TMEM reads of this accumulator are done
+          if (ch + 2 >= BLOCK_N / 64) {       // this warp's last TMEM read of the accumulator
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0); }
@@ -321,10 +331,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (cbase + j < p.cout_valid) o[(long long)(cbase + j) * hw] = f[j];
             }
           } else {
-            // staging buffer `sbuf` was last read by the TMA store issued two chunks ago
-            if (issuer) bulk_wait_group_read<1>();
-            named_bar_sync(1, kEpiWarps * 32);
-            uint8_t* srow = staging + sbuf * kStagingBytes + row * 128;
+            // this warpgroup's staging tile was last read by the TMA store of its previous chunk
+            if (issuer) bulk_wait_group_read<0>();
+            named_bar_sync(bar_a, 128);
+            uint8_t* srow = stage_out + row * 128;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               uint4 pk;
@@ -339,9 +349,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<uint4*>(srow + ((u ^ (row & 7)) << 4)) = pk;   // 128-byte swizzle
             }
             fence_proxy_async_smem();
-            named_bar_sync(2, kEpiWarps * 32);
+            named_bar_sync(bar_b, 128);
             if (issuer) {
-              tma_store_4d(&tmY, staging + sbuf * kStagingBytes, cbase, w0, h0, n0);
+              tma_store_4d(&tmY, stage_out, cbase, w0, h0, n0);
               bulk_commit_group();
             }
             if (p.colsum) {
@@ -349,14 +359,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // Thread = (column, half of the rows); a warp reads 32 consecutive channels of one row
               // (conflict-free under the 128-byte swizzle).  Rows 0-63 / 64-127 are separate partial rows
               // (with TN == 2 they are two different images).
-              const int col = threadIdx.x & 63, half = threadIdx.x >> 6;
-              const uint8_t* sb0 = staging + sbuf * kStagingBytes + (col & 7) * 2;
+              const int col = etid & 63, half = etid >> 6;
+              const uint32_t sb0 = smem_u32(stage_out) + (col & 7) * 2;
               const int unit = col >> 3;
               float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 8
               for (int r = half * 64; r < half * 64 + 64; ++r) {
-                const uint16_t raw = *reinterpret_cast<const uint16_t*>(sb0 + r * 128 + ((unit ^ (r & 7)) << 4));
-                const float v = __uint_as_float((uint32_t)raw << 16);
+                uint32_t raw;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw) : "r"(sb0 + r * 128 + ((unit ^ (r & 7)) << 4)));
+                const float v = __uint_as_float(raw << 16);
                 s1 += v;
                 s2 = fmaf(v, v, s2);
               }
@@ -368,7 +379,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *dst = make_float2(s1, s2);
               }
             }
-            sbuf ^= 1;
           }
         }
         }  // if (finish)
@@ -380,7 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        if (valid && p.y_nchw) {
+        if (valid && p.y_nchw && wg == 0) {
           const long long hw = (long long)p.H * p.W;
           float* o = p.y_nchw + ((long long)n * p.cout_valid) * hw + (long long)h * p.W + w;
 #pragma unroll
@@ -402,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
