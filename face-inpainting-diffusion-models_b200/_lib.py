@@ -72,6 +72,8 @@ SYMBOLS = {
     "fidm_sampler_step": (C.c_int, [_P(StepArgs), vp]),
     "fidm_pack_nchw_to_nhwc": (C.c_int, [_P(PackArgs), vp]),
     "fidm_unpack_nhwc_to_nchw": (C.c_int, [vp, i32, i32, fp, i32, i32, i32, vp]),
+    "fidm_prepare_inputs_u8": (C.c_int, [vp, vp, fp, fp, fp, fp, i32, i32, vp]),
+    "fidm_blend_to_u8": (C.c_int, [fp, fp, fp, vp, i32, i32, vp]),
     "fidm_timestep_embedding": (C.c_int, [fp, fp, fp, i32, i32, vp]),
     "fidm_linear_small": (C.c_int, [fp, vp, i32, fp, fp, i32, i32, i32, i32, vp]),
     "fidm_groupnorm_silu_nhwc": (C.c_int, [_P(GnArgs), vp]),

@@ -168,3 +168,76 @@ extern "C" int fidm_repack_weight_oihw_to_krsc(const float* w, void* dst, int32_
   FIDM_CHECK_LAUNCH("repack_weight");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// I/O adapters: the dataset / PNG conventions of the reference as GPU kernels.
+// ------------------------------------------------------------------------------------------------
+namespace fidm {
+
+// data/dataset.py:38-42,130-142: image = (u8/255 - 0.5)/0.5, mask = (gray/255 < 0.5) ? 1 : 0 (1 = inpaint),
+// masked_image = image * (1 - mask), keep = 1 - mask.  uint8 NHWC in, fp32 NCHW out; one rounding per torch op.
+__global__ void __launch_bounds__(256) prepare_inputs_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk,
+                                                              float* __restrict__ image, float* __restrict__ masked,
+                                                              float* __restrict__ mask, float* __restrict__ keep, int batch,
+                                                              int hw) {
+  const long long total = (long long)batch * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw), px = (int)(i % hw);
+    const float m = (__fdiv_rn((float)msk[i], 255.0f) < 0.5f) ? 1.0f : 0.0f;
+    const float k = __fsub_rn(1.0f, m);
+    mask[i] = m;
+    keep[i] = k;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)img[i * 3 + c], 255.0f), 0.5f), 0.5f);
+      const long long o = ((long long)b * 3 + c) * hw + px;
+      image[o] = v;
+      masked[o] = __fmul_rn(v, k);
+    }
+  }
+}
+
+// test_inp_ddim_100.py:693-696 then :33-41: out = toU8(sample * mask + gt * (1 - mask)), NCHW fp32 -> NHWC uint8.
+__global__ void __launch_bounds__(256) blend_to_u8_kernel(const float* __restrict__ sample, const float* __restrict__ gt,
+                                                           const float* __restrict__ mask, uint8_t* __restrict__ out,
+                                                           int batch, int hw) {
+  const long long total = (long long)batch * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw), px = (int)(i % hw);
+    const float m = mask ? mask[i] : 1.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long o = ((long long)b * 3 + c) * hw + px;
+      float v = sample[o];
+      if (mask) v = __fadd_rn(__fmul_rn(v, m), __fmul_rn(gt[o], __fsub_rn(1.0f, m)));
+      v = __fmul_rn(__fadd_rn(v, 1.0f), 127.5f);
+      v = fminf(fmaxf(v, 0.0f), 255.0f);
+      out[i * 3 + c] = (uint8_t)v;                     // truncation, as Tensor.to(torch.uint8)
+    }
+  }
+}
+
+}  // namespace fidm
+
+extern "C" int fidm_prepare_inputs_u8(const uint8_t* image_u8_nhwc, const uint8_t* mask_u8, float* image, float* masked_image,
+                                      float* mask, float* keep_mask, int32_t batch, int32_t hw, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(image_u8_nhwc && mask_u8 && image && masked_image && mask && keep_mask && batch > 0 && hw > 0, FIDM_E_BADARG,
+               "prepare_inputs_u8: bad args");
+  prepare_inputs_kernel<<<grid_for((long long)batch * hw), 256, 0, (cudaStream_t)stream>>>(image_u8_nhwc, mask_u8, image,
+                                                                                          masked_image, mask, keep_mask, batch, hw);
+  FIDM_CHECK_LAUNCH("prepare_inputs_u8");
+  return 0;
+}
+
+extern "C" int fidm_blend_to_u8(const float* sample, const float* gt, const float* mask, uint8_t* out_u8_nhwc, int32_t batch,
+                                int32_t hw, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(sample && out_u8_nhwc && batch > 0 && hw > 0 && ((mask == nullptr) == (gt == nullptr)), FIDM_E_BADARG,
+               "blend_to_u8: bad args");
+  blend_to_u8_kernel<<<grid_for((long long)batch * hw), 256, 0, (cudaStream_t)stream>>>(sample, gt, mask, out_u8_nhwc, batch, hw);
+  FIDM_CHECK_LAUNCH("blend_to_u8");
+  return 0;
+}

@@ -173,3 +173,27 @@ def attention(qkv, heads, *, out=None, impl="auto"):
     fn = L.lib().fidm_attention_qkv_nhwc_bf16 if impl == "tc" else L.lib().fidm_attention_qkv_nhwc_simt
     L.check(fn(C.byref(a), L.stream()), "attention/" + impl)
     return y
+
+
+def prepare_inputs_u8(image_u8, mask_u8):
+    """uint8 images [N,H,W,3] + grayscale masks [N,H,W] (black = inpaint) -> the reference's dataset batch
+    (data/dataset.py:130-150): dict(image, masked_image, mask, gt_keep_mask) as fp32 NCHW."""
+    n, h, w, _ = image_u8.shape
+    image_u8, mask_u8 = image_u8.contiguous(), mask_u8.contiguous()
+    dev = image_u8.device
+    image = torch.empty(n, 3, h, w, device=dev)
+    masked = torch.empty(n, 3, h, w, device=dev)
+    mask = torch.empty(n, 1, h, w, device=dev)
+    keep = torch.empty(n, 1, h, w, device=dev)
+    L.check(L.lib().fidm_prepare_inputs_u8(L.ptr(image_u8), L.ptr(mask_u8), L.ptr(image), L.ptr(masked), L.ptr(mask),
+                                           L.ptr(keep), n, h * w, L.stream()), "prepare_inputs_u8")
+    return {"image": image, "masked_image": masked, "mask": mask, "gt_keep_mask": keep}
+
+
+def blend_to_u8(sample, gt=None, mask=None):
+    """toU8(sample * mask + gt * (1 - mask)) (test_inp_ddim_100.py:33-41, 693-696): [N,H,W,3] uint8."""
+    n, _, h, w = sample.shape
+    out = torch.empty(n, h, w, 3, device=sample.device, dtype=torch.uint8)
+    L.check(L.lib().fidm_blend_to_u8(L.ptr(sample.float().contiguous()), L.ptr(gt), L.ptr(mask), L.ptr(out), n, h * w,
+                                     L.stream()), "blend_to_u8")
+    return out

@@ -126,6 +126,16 @@ int fidm_pack_nchw_to_nhwc(const fidm_pack_args* a, fidm_stream_t stream);
 int fidm_unpack_nhwc_to_nchw(const void* src, int32_t src_dtype, int32_t ld_src, float* dst,
                              int32_t batch, int32_t hw, int32_t channels, fidm_stream_t stream);
 
+/* I/O adapters (the reference does these on the CPU in its DataLoader / save path):
+ *   fidm_prepare_inputs_u8 : data/dataset.py:38-42,130-142 -- image = (u8/255 - 0.5)/0.5, mask = (gray/255 < 0.5)
+ *                            (1 = inpaint), masked_image = image*(1-mask), keep = 1-mask; uint8 NHWC -> fp32 NCHW.
+ *   fidm_blend_to_u8       : test_inp_ddim_100.py:693-696 + toU8 :33-41 -- ((s*m + gt*(1-m) + 1)*127.5).clamp(0,255)
+ *                            -> uint8 NHWC (gt = mask = NULL: no blend). */
+int fidm_prepare_inputs_u8(const uint8_t* image_u8_nhwc, const uint8_t* mask_u8, float* image, float* masked_image,
+                           float* mask, float* keep_mask, int32_t batch, int32_t hw, fidm_stream_t stream);
+int fidm_blend_to_u8(const float* sample, const float* gt, const float* mask, uint8_t* out_u8_nhwc, int32_t batch,
+                     int32_t hw, fidm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  timestep path.  timestep_embedding (nn.py:51-61; `freqs` is the host-computed table exactly
  * as the reference computes it on the CPU) and small-batch Linear with optional SiLU on the input

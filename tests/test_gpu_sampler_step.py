@@ -136,3 +136,29 @@ def test_timestep_path(cuda_lib):
         y16 = ops.linear_small(x, w.bfloat16(), b)
         want16 = torch.nn.functional.linear(x.double(), w.bfloat16().double(), b.double()).float()
         assert torch.allclose(y16, want16, atol=2e-5, rtol=1e-5)
+
+
+def test_io_adapters_match_reference_conventions(cuda_lib):
+    """data/dataset.py:38-42,130-142 (ToTensor + Normalize, mask < 0.5) and toU8 / final blend
+    (test_inp_ddim_100.py:33-41, 693-696), bit-exact against the same torch ops."""
+    from fidm_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (3, 32, 24, 3), dtype=torch.uint8, generator=g).cuda()
+    msk = torch.randint(0, 256, (3, 32, 24), dtype=torch.uint8, generator=g).cuda()
+    d = ops.prepare_inputs_u8(img, msk)
+    # the reference's DataLoader runs these ops on the CPU (true IEEE division; CUDA torch multiplies by 1/255)
+    t = img.cpu().permute(0, 3, 1, 2).float().div(255)
+    want_img = ((t - 0.5) / 0.5).cuda()
+    want_mask = (msk.cpu().float().div(255)[:, None] < 0.5).float().cuda()
+    assert torch.equal(d["image"], want_img) and torch.equal(d["mask"], want_mask)
+    assert torch.equal(d["masked_image"], want_img * (1 - want_mask))
+    assert torch.equal(d["gt_keep_mask"], 1 - want_mask)
+    sample = torch.randn(3, 3, 32, 24, device="cuda") * 1.5
+    out = ops.blend_to_u8(sample, d["image"], d["mask"])
+    res = sample * d["mask"] + d["image"] * (1 - d["mask"])
+    want = ((res + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(out, want)
+    # (the reference's toU8 truncates, so known pixels come back within one code of the original bytes)
+    keep = (1 - d["mask"]).bool().expand(-1, 3, -1, -1).permute(0, 2, 3, 1)
+    assert (out[keep].int() - img[keep].int()).abs().max().item() <= 1
+    assert torch.equal(ops.blend_to_u8(sample), ((sample + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
