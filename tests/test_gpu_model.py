@@ -239,3 +239,26 @@ def test_script_ddim_step_bit_exact(cuda_lib):
                         inject_noise=n.to(DEV), script_table=table, want_next=True, want_sample=True)
             assert torch.equal(r["sample"].cpu(), img), (eta, k)
             assert torch.equal(r["x_next"].cpu(), want), (eta, k)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (3, 64, 64), (2, 64, 32), (5, 32, 96)])
+def test_batch_and_shape_edge_cases(cuda_lib, B, H, W):
+    """Odd batches (pixel tiles that straddle / overhang images), non-square and non-power-of-two sizes:
+    fp32 mode to 2e-5, bf16 mode to 1e-2 of the CPU oracle."""
+    import fidm_b200 as F
+    from fidm_b200.utils.synth import synth_state_dict
+    from oracle import unet_oracle as uor
+    cfg = F.CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=5)
+    g = torch.Generator().manual_seed(B * 100 + W)
+    x = torch.randn(B, 3, H, W, generator=g)
+    gt = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.6).float()
+    t = torch.randint(0, 50, (B,), generator=g)
+    with torch.no_grad():
+        want = uor.inpaint_forward(sd, cfg, x, t, gt * (1 - mask), mask)
+    for precision, tol in (("fp32", 2e-5), ("bf16", 1e-2)):
+        m = _model(cfg, sd, precision)
+        out = m(x.to(DEV), t.to(DEV), masked_image=(gt * (1 - mask)).to(DEV), mask=mask.to(DEV))
+        assert out.shape == want.shape
+        assert rel_l2(out.cpu(), want) < tol, (precision, B, H, W, rel_l2(out.cpu(), want))
