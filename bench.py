@@ -280,8 +280,11 @@ def main():
         "clocks": clk.summary(),
     }
 
+    line["config"]["operand_dtypes"] = ("residual stream / qkv / attention bf16; normalized conv operands and their "
+                                        "weights fp16; fp32 accumulation, statistics, softmax and sampler state")
     if rank == 0:
         line["roofline"] = dominant_kernel_roofline(ops, dev, pk, B)
+        line["hbm_kernels"] = hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S)
         if world == 1 and not args.no_cpu_baseline:
             evals = 2 if S == 256 else 5
             times, cores = cpu_oracle_sample(wl, evals + 1)
@@ -293,6 +296,61 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _time_launches(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S):
+    """The two HBM-bound kernels against the measured copy bandwidth: K2 GroupNorm+SiLU apply on the largest
+    activation (256 channels at full resolution, statistics from the producer's fused column sums) and K4, the
+    fused sampler step (DDIM eta=0 update + injection: 64 B per pixel)."""
+    from fidm_b200 import _lib as L
+    Cc = 256
+    x = torch.randn(B, S, S, Cc, device=dev).bfloat16()
+    y = torch.empty(B, S, S, Cc, device=dev, dtype=torch.float16)
+    gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+    xf = x.float()
+    cs = torch.stack([xf.sum(dim=(1, 2)), (xf * xf).sum(dim=(1, 2))], dim=-1).contiguous()
+    del xf
+    ms_gn = _time_launches(lambda: ops.groupnorm_silu(x, gamma, beta, out=y, chansum=cs))
+    by_gn = 2.0 * x.numel() * 2
+    xs = torch.randn(B, 3, S, S, device=dev)
+    mo = torch.randn(B, 6, S, S, device=dev)
+    gt = torch.rand(B, 3, S, S, device=dev)
+    keep = (torch.rand(B, 1, S, S, device=dev) > 0.5).float()
+    n = torch.randn(B, 3, S, S, device=dev)
+    T = diffusion.num_timesteps
+    ms_k4 = _time_launches(lambda: diffusion._step(L.STEP_UPDATE_INJECT, xs, t=T // 2, t_inject=T // 2 - 1, model_out=mo,
+                                                   gt=gt, keep=keep, inject_noise=n, ddim=True, want_next=True), n=50)
+    by_k4 = 64.0 * B * S * S
+    # the same kernel on 64 images (268 MB per launch), where the launch latency no longer dominates
+    B2 = 64
+    xs2, mo2 = torch.randn(B2, 3, S, S, device=dev), torch.randn(B2, 6, S, S, device=dev)
+    gt2, n2 = torch.rand(B2, 3, S, S, device=dev), torch.randn(B2, 3, S, S, device=dev)
+    keep2 = (torch.rand(B2, 1, S, S, device=dev) > 0.5).float()
+    ms_k4b = _time_launches(lambda: diffusion._step(L.STEP_UPDATE_INJECT, xs2, t=T // 2, t_inject=T // 2 - 1, model_out=mo2,
+                                                    gt=gt2, keep=keep2, inject_noise=n2, ddim=True, want_next=True), n=50)
+    by_k4b = 64.0 * B2 * S * S
+    return {"groupnorm_silu_apply": {"bytes_per_launch": by_gn, "ms_per_launch": ms_gn, "achieved_gbs": by_gn / ms_gn / 1e6,
+                                     "frac_of_hbm_peak": by_gn / ms_gn / 1e6 / pk["hbm_gbs"]},
+            "sampler_step": {"bytes_per_launch": by_k4, "ms_per_launch": ms_k4, "achieved_gbs": by_k4 / ms_k4 / 1e6,
+                             "frac_of_hbm_peak": by_k4 / ms_k4 / 1e6 / pk["hbm_gbs"],
+                             "note": "34 MB per launch at batch 8: launch-latency bound (includes the Python launcher)"},
+            "sampler_step_batch64": {"bytes_per_launch": by_k4b, "ms_per_launch": ms_k4b,
+                                     "achieved_gbs": by_k4b / ms_k4b / 1e6,
+                                     "frac_of_hbm_peak": by_k4b / ms_k4b / 1e6 / pk["hbm_gbs"]},
+            "peak_gbs": pk["hbm_gbs"], "peak_src": pk["src"]}
 
 
 def dominant_kernel_roofline(ops, dev, pk, B):
