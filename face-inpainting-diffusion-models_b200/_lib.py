@@ -55,7 +55,8 @@ class ConvArgs(C.Structure):
                 ("bias", fp), ("row_add", fp), ("ld_row_add", i32),
                 ("residual", vp), ("ld_res", i32), ("y", vp), ("ld_y", i32),
                 ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp),
-                ("splitk_ws", vp), ("splitk_ws_bytes", C.c_int64)]
+                ("splitk_ws", vp), ("splitk_ws_bytes", C.c_int64),
+                ("gn_coef", fp), ("ld_gn_coef", i32)]
 
 
 class AttnArgs(C.Structure):
@@ -79,7 +80,9 @@ SYMBOLS = {
     "fidm_groupnorm_silu_nhwc": (C.c_int, [_P(GnArgs), vp]),
     "fidm_groupnorm_workspace_bytes": (C.c_int64, [i32, i32]),
     "fidm_groupnorm_reduce_colsum": (C.c_int, [fp, i32, i32, i32, fp, i32, i32, vp]),
+    "fidm_groupnorm_silu_coeff": (C.c_int, [_P(GnArgs), fp, i32, vp]),
     "fidm_conv_colsum_slots": (C.c_int, [i32, i32]),
+    "fidm_conv_gn_fusable": (C.c_int, [i32, i32, i32, i32, i32, i32, i32]),
     "fidm_conv2d_nhwc_bf16": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_conv2d_nhwc_simt": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_attention_qkv_nhwc_bf16": (C.c_int, [_P(AttnArgs), vp]),
@@ -106,7 +109,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.fidm_abi_version() != 1:
+        if handle.fidm_abi_version() != 2:
             raise FidmError("libfidm_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -1,0 +1,543 @@
+// K1h: 3x3 convolution with the producer's GroupNorm(32) [* (1+scale) + shift] + SiLU applied in the operand path.
+//
+//   D[M = B*H*W pixels, N = Cout] = sum over taps (r,s) and 64-channel slices of
+//                                   act(X)_{r,s}[M, 64] * W[N, (r,s), 64]^T ,   act(x) = silu(x * A[n][c] + B[n][c])
+//
+// Replaces, for the convolutions that follow a GroupNorm, BOTH the normalisation pass and the conv
+// (nn.py:151-153, 173-176, 203-207: in_layers / out_layers of ResBlock).  The separate GroupNorm "apply" pass
+// (2 B read + 2 B written per element, 13 % of a UNet evaluation) disappears, and the activation tensor is
+// fetched once per 64-channel slice instead of once per tap:
+//
+//   * An M tile is an 8 x 16 box of output pixels of one image.  For every 64-channel slice ONE TMA box load
+//     fetches the 10 x 18 halo tile of the RAW bf16 stream (out-of-image pixels are zero-filled by the hardware).
+//   * Four transform warps read the halo tile once, apply h = x*A' + B' ; y = h + h*tanh(h)  (= silu(x*A + B) with
+//     A' = A/2, B' = B/2: one MUFU op), force the conv's zero padding (out-of-image pixels are 0 AFTER the
+//     activation), and write three column-shifted copies (s = 0,1,2) of [18 rows][8 pixels][64 ch] 16-bit in the
+//     canonical K-major 128-byte-swizzled UMMA layout.  A row of a copy is exactly one 1024-byte swizzle atom, so
+//     tap (r,s) is the descriptor  copy_s + r * 1024  -- always atom-aligned: nine MMAs per halo tile.
+//   * Weights stream through a TMA ring as in K1; the optional 1x1 skip source (nn.py:184,212) rides the same
+//     ring (one stage for its A box, one for its weights) as extra K iterations.
+//   * CTA pair (cta_group::2): each CTA transforms its own 128 pixel rows and stages half of the weight tile.
+//   * Epilogue = K1's (bias, timestep row, residual, bf16 TMA store into concat slices, fused GroupNorm statistics
+//     of the output).
+//
+// Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-11 transform, 12 weight-ring TMA producer,
+// 13 MMA issuer (+ TMEM owner), 14 halo TMA producer.  Register budgets are rebalanced with setmaxnreg.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_host.cuh"
+#include "sm100_primitives.cuh"
+
+namespace fidm {
+using namespace sm100;
+
+struct ConvHaloParams {
+  int B, H, W;
+  int tiles_w, tiles_h;     // 8 x 16 pixel boxes per image
+  int n_blocks;             // Cout / BLOCK_N
+  int kc1, cin1;            // Cin / 64, Cin
+  int kc2;                  // Cin2 / 64 of the optional 1x1 second source
+  const float2* coef; int ld_coef;   // [B][ld_coef] (A/2, B/2) per (image, input channel)
+  const float* bias;
+  const float* row_add; int ld_row_add;
+  const __nv_bfloat16* residual; int ld_res;
+  float* colsum; int colsum_slots; int cout;
+};
+
+namespace halo {
+constexpr int kThreads = 512;
+constexpr int kEpiWarps = 8;
+constexpr int kTW = 8, kTH = 16;                       // output pixel box of one CTA
+constexpr int kHW = kTW + 2, kHH = kTH + 2;            // halo tile
+constexpr int kHaloPix = kHW * kHH;                    // 180
+constexpr int kRawBytes = kHaloPix * 128;              // 23040 (TMA transaction size)
+constexpr int kRawStride = 23 * 1024;                  // buffers stay 1024-byte aligned (swizzle atom)
+constexpr int kCopyBytes = kHH * 1024;                 // [18 rows][8 pixels][128 B]
+constexpr int kRingStageBytes = 16384;                 // one weight half-tile (<= 128 rows x 128 B) or one A2 box
+constexpr int kRingStages = 5;
+constexpr int kStagingBytes = 128 * 128;
+constexpr int kOffRaw = 0;
+constexpr int kOffCopy = kOffRaw + 2 * kRawStride;
+constexpr int kOffRing = kOffCopy + 3 * kCopyBytes;
+constexpr int kOffStaging = kOffRing + kRingStages * kRingStageBytes;
+constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
+constexpr int kSmemBytes = kOffBars + 256 + 1024;
+static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0 && kOffStaging % 1024 == 0, "swizzle-atom alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kVecPerThread = (kHaloPix * 8 + 127) / 128;   // 16-byte vectors of one halo tile per transform thread (12)
+}  // namespace halo
+
+__device__ __forceinline__ uint32_t ld_shared_u32x4(uint32_t addr, uint32_t& y, uint32_t& z, uint32_t& w) {
+  uint32_t x;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+  return x;
+}
+__device__ __forceinline__ void st_shared_u32x4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// release at cluster scope: the generic-proxy writes (made visible to the async proxy by fence.proxy.async) of this
+// CTA must be ordered before the leader's MMA thread observes the arrival.
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fidm: mbarrier wait (cluster) timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// silu(x*A + B) of two packed bf16 values -> two packed 16-bit results (fp16 or bf16).
+template <bool OUT_F16>
+__device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, float a1, float b1) {
+  const float h0 = fmaf(__uint_as_float(raw << 16), a0, b0);
+  const float h1 = fmaf(__uint_as_float(raw & 0xFFFF0000u), a1, b1);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  const float y0 = fmaf(h0, t0, h0), y1 = fmaf(h1, t1, h1);
+  if (OUT_F16) {
+    const __half2 o = __floats2half2_rn(y0, y1);
+    return *reinterpret_cast<const uint32_t*>(&o);
+  }
+  const __nv_bfloat162 o = __floats2bfloat162_rn(y0, y1);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+
+template <int BLOCK_N, bool OUT_F16>
+__global__ void __launch_bounds__(halo::kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
+  using namespace halo;
+  constexpr int kBBytes = (BLOCK_N / 2) * 128;           // this CTA's half of one weight tile
+  constexpr int kTmemCols = 2 * BLOCK_N;
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  static_assert(kBBytes <= kRingStageBytes, "ring stage too small");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* const raw_buf = smem + kOffRaw;
+  uint8_t* const copy_buf = smem + kOffCopy;
+  uint8_t* const ring = smem + kOffRing;
+  uint8_t* const staging = smem + kOffStaging;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* const raw_full = bars;              // [2]  TMA -> transform
+  uint64_t* const raw_empty = bars + 2;         // [2]  transform -> halo producer
+  uint64_t* const a_full = bars + 4;            // [3]  transform (both CTAs) -> MMA issuer   (leader's copy is used)
+  uint64_t* const a_empty = bars + 7;           // [3]  MMA commit -> transform (multicast to both CTAs)
+  uint64_t* const ring_full = bars + 10;        // [kRingStages]
+  uint64_t* const ring_empty = bars + 10 + kRingStages;
+  uint64_t* const tmem_full = bars + 10 + 2 * kRingStages;    // [2]
+  uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();          // rank 0 = leader (issues the MMAs)
+  const int unit = (int)(blockIdx.x >> 1);
+  const int n_units = (int)(gridDim.x >> 1);
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = tiles_img * p.B;                   // even (tiles_w is even)
+  const int total_units = (m_tiles >> 1) * p.n_blocks;   // (pair of horizontally adjacent boxes) x N block
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmRaw);
+    tma_prefetch_desc(&tmB);
+    if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 13) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 2); mbar_init(&ring_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_slot, kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 12 && lane == 0) {
+      // ================================================================ weight / second-source ring producer
+      int stage = 0; uint32_t phase = 0;
+      auto acquire = [&](uint32_t bytes_per_cta) {
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        if (cta_rank == 0) mbar_expect_tx(&ring_full[stage], 2 * bytes_per_cta);   // both CTAs' bytes land on the leader
+        else mbar_arrive_cluster(&ring_full[stage], 0);
+      };
+      auto advance = [&]() { if (++stage == kRingStages) { stage = 0; phase ^= 1; } };
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        const int n_blk = wu % p.n_blocks, m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+        const int w0 = (m_blk % p.tiles_w) * kTW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+        const int n0 = m_blk / tiles_img;
+        const int co0 = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+        for (int kc = 0; kc < p.kc1; ++kc)
+          for (int s = 0; s < 3; ++s)
+            for (int r = 0; r < 3; ++r) {
+              acquire(kBBytes);
+              tma_load_2d_2sm(&tmB, &ring_full[stage], ring + stage * kRingStageBytes, (r * 3 + s) * p.cin1 + kc * 64, co0);
+              advance();
+            }
+        for (int kc = 0; kc < p.kc2; ++kc) {
+          acquire(kTW * kTH * 128);
+          tma_load_4d_2sm(&tmA2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, w0, h0, n0);
+          advance();
+          acquire(kBBytes);
+          tma_load_2d_2sm(&tmB2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
+          advance();
+        }
+      }
+    } else if (warp == 14 && lane == 0) {
+      // ================================================================ halo producer (this CTA's own 10 x 18 boxes)
+      uint32_t g = 0;
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+        const int w0 = (m_blk % p.tiles_w) * kTW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+        const int n0 = m_blk / tiles_img;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          const uint32_t rb = g & 1u;
+          mbar_wait(&raw_empty[rb], ((g >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&raw_full[rb], kRawBytes);
+          tma_load_4d(&tmRaw, &raw_full[rb], raw_buf + rb * kRawStride, kc * 64, w0 - 1, h0 - 1, n0);
+        }
+      }
+    } else if (warp == 13 && lane == 0 && cta_rank == 0) {
+      // ================================================================ MMA issuer (leader CTA)
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(256, BLOCK_N);
+      constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(256, BLOCK_N) : idesc_bf16;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t g = 0;
+      const uint32_t copy_addr = smem_u32(copy_buf), ring_addr = smem_u32(ring);
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        uint32_t accum = 0;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait_cluster(&a_full[s], g & 1u);
+            tc_fence_after();
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&ring_full[stage], phase);
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(copy_addr + s * kCopyBytes + r * 1024);
+              const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_main, accum);
+                accum = 1;
+              }
+              umma_commit_2sm(&ring_empty[stage], 3);
+              if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_2sm(&a_empty[s], 3);      // copy s may be overwritten (in both CTAs) once these MMAs have read it
+          }
+        }
+        for (int kc = 0; kc < p.kc2; ++kc) {
+          const int st_a = stage;
+          mbar_wait(&ring_full[stage], phase);
+          if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+          mbar_wait(&ring_full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(ring_addr + st_a * kRingStageBytes);
+          const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_bf16, accum);
+            accum = 1;
+          }
+          umma_commit_2sm(&ring_empty[st_a], 3);
+          umma_commit_2sm(&ring_empty[stage], 3);
+          if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc], 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ==================================================================== transform warps (8-11)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    const int tt = (int)threadIdx.x - 256;
+    const int j = tt & 7;                 // 16-byte channel chunk (8 channels) of the 64-channel slice
+    const int pl = tt >> 3;               // pixel lane: this thread owns halo pixels pl, pl + 16, ...
+    const uint32_t raw_addr = smem_u32(raw_buf), copy_addr = smem_u32(copy_buf);
+    uint32_t g = 0;
+    for (int wu = unit; wu < total_units; wu += n_units) {
+      const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+      const int w0 = (m_blk % p.tiles_w) * kTW;
+      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+      const int n0 = m_blk / tiles_img;
+      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+      for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+        float4 c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A,B) of channels 2q, 2q+1 of this chunk
+        const uint32_t rb = g & 1u;
+        mbar_wait(&raw_full[rb], (g >> 1) & 1u);
+        const uint32_t rbase = raw_addr + rb * kRawStride;
+        uint4 v[kVecPerThread];
+#pragma unroll
+        for (int i = 0; i < kVecPerThread; ++i) {
+          const int px = pl + 16 * i;
+          v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (px < kHaloPix) {
+            const int y = px / kHW, x = px - y * kHW;
+            const bool inside = (unsigned)(w0 - 1 + x) < (unsigned)p.W && (unsigned)(h0 - 1 + y) < (unsigned)p.H;
+            if (inside) {   // the conv zero-pads the ACTIVATED tensor: out-of-image pixels stay 0
+              uint32_t r1, r2, r3;
+              const uint32_t r0 = ld_shared_u32x4(rbase + px * 128 + ((j ^ (px & 7)) << 4), r1, r2, r3);
+              v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+              v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+              v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+              v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          // copy s holds, for halo row y, the pixels x = s .. s + 7 as the 8 rows of one swizzle atom
+          mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+          const uint32_t cbase = copy_addr + s * kCopyBytes;
+#pragma unroll
+          for (int i = 0; i < kVecPerThread; ++i) {
+            const int px = pl + 16 * i;
+            if (px < kHaloPix) {
+              const int y = px / kHW, x = px - y * kHW;
+              const int xx = x - s;
+              if ((unsigned)xx < 8u) st_shared_u32x4(cbase + (y * 8 + xx) * 128 + ((j ^ xx) << 4), v[i]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(7, 128);
+          if (tt == 0) {
+            if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the halo tile
+            mbar_arrive_cluster_release(&a_full[s], 0);
+          }
+        }
+      }
+    }
+  } else {
+    // ==================================================================== epilogue (warps 0-7), as in K1
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int wg = warp >> 2, qw = warp & 3;          // warp (qw) may only touch TMEM lanes [32 qw, 32 qw + 32)
+    const int row = qw * 32 + lane;                   // TMEM lane == pixel row of this CTA's box
+    const uint32_t lane_sel = (uint32_t)(qw * 32) << 16;
+    const int wl = row & 7, hl = row >> 3;
+    const bool issuer = (row == 0);
+    const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
+    uint8_t* const stage_out = staging + wg * kStagingBytes;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int wu = unit; wu < total_units; wu += n_units) {
+      const int n_blk = wu % p.n_blocks, m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+      const int w0 = (m_blk % p.tiles_w) * kTW;
+      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+      const int n = m_blk / tiles_img;
+      const int co0 = n_blk * BLOCK_N;
+      const long long pix = ((long long)n * p.H + (h0 + hl)) * p.W + (w0 + wl);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
+        const int cbase = co0 + ch * 64;
+        float f[64];
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_acc + ch * 64, v0);
+          tmem_ld_32x32(t_acc + ch * 64 + 32, v1);
+          tc_wait_ld();
+          if (ch + 2 >= BLOCK_N / 64) {       // this warp's last TMEM read of the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          }
+#pragma unroll
+          for (int q = 0; q < 32; ++q) { f[q] = __uint_as_float(v0[q]); f[32 + q] = __uint_as_float(v1[q]); }
+        }
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 t = __ldg(b4 + q);
+            f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+          }
+        }
+        if (p.row_add) {
+          const float4* r4 = reinterpret_cast<const float4*>(p.row_add + (long long)n * p.ld_row_add + cbase);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 t = __ldg(r4 + q);
+            f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+          }
+        }
+        if (p.residual) {
+          const uint4* rs = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + cbase);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 t = __ldg(rs + q);
+            const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[8 * q + 2 * e] += __uint_as_float(u[e] << 16);
+              f[8 * q + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
+            }
+          }
+        }
+        // this warpgroup's staging tile was last read by the TMA store of its previous chunk
+        if (issuer) bulk_wait_group_read<0>();
+        named_bar_sync(bar_a, 128);
+        uint8_t* srow = stage_out + row * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint4 pk;
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(f[8 * u + 0], f[8 * u + 1]);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(f[8 * u + 2], f[8 * u + 3]);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * u + 4], f[8 * u + 5]);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(f[8 * u + 6], f[8 * u + 7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&b0);
+          pk.y = *reinterpret_cast<uint32_t*>(&b1);
+          pk.z = *reinterpret_cast<uint32_t*>(&b2);
+          pk.w = *reinterpret_cast<uint32_t*>(&b3);
+          *reinterpret_cast<uint4*>(srow + ((u ^ (row & 7)) << 4)) = pk;   // 128-byte swizzle
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_b, 128);
+        if (issuer) {
+          tma_store_4d(&tmY, stage_out, cbase, w0, h0, n);
+          bulk_commit_group();
+        }
+        if (p.colsum) {
+          // Fused GroupNorm statistics of the OUTPUT (for its consumer): per-channel (sum, sum of squares) of the
+          // bf16 tile just staged; rows 0-63 / 64-127 are separate partial rows (fixed-order fold later).
+          const int col = row & 63, half = row >> 6;
+          const uint32_t sb0 = smem_u32(stage_out) + (col & 7) * 2;
+          const int cu = col >> 3;
+          float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 8
+          for (int r = half * 64; r < half * 64 + 64; ++r) {
+            uint32_t rawv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rawv) : "r"(sb0 + r * 128 + ((cu ^ (r & 7)) << 4)));
+            const float val = __uint_as_float(rawv << 16);
+            s1 += val;
+            s2 = fmaf(val, val, s2);
+          }
+          const int slot = (m_blk % tiles_img) * 2 + half;
+          float2* dst = reinterpret_cast<float2*>(p.colsum) + ((long long)n * p.colsum_slots + slot) * p.cout + cbase + col;
+          *dst = make_float2(s1, s2);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+bool conv_halo_supported(const fidm_conv_args& a) {
+  return a.ksize == 3 && a.stride == 1 && a.height % halo::kTH == 0 && a.width % (2 * halo::kTW) == 0 &&
+         a.cin % 64 == 0 && a.cin > 0 && a.cout % 128 == 0 && !a.y_nchw_f32 &&
+         (a.dtype == FIDM_F16 || a.dtype == FIDM_BF16);
+}
+
+template <int BLOCK_N, bool OUT_F16>
+static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
+  using namespace halo;
+  ConvHaloParams p;
+  p.B = a.batch; p.H = a.height; p.W = a.width;
+  p.tiles_w = a.width / kTW; p.tiles_h = a.height / kTH;
+  p.n_blocks = a.cout / BLOCK_N;
+  p.kc1 = a.cin / 64; p.cin1 = a.cin;
+  p.kc2 = a.x2 ? a.cin2 / 64 : 0;
+  p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
+  p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
+  p.colsum = a.colsum; p.cout = a.cout;
+  p.colsum_slots = p.tiles_w * p.tiles_h * 2;
+
+  CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY;
+  int rc;
+  // the raw stream is bf16; only the element SIZE matters to the copy engine
+  if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHW, kHH, 1, 0))) return rc;
+  if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, OUT_F16 ? 1 : 0))) return rc;
+  if (a.x2) {
+    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kTW, kTH, 1, 0))) return rc;
+    if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N / 2, 0))) return rc;
+  } else {
+    tmA2 = tmRaw; tmB2 = tmB;
+  }
+  if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kTW, kTH, 1, 0))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, OUT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int units = (p.tiles_w * p.tiles_h * p.B / 2) * p.n_blocks;
+  const int slots = num_sms() / 2;
+  const int grid = (units < slots ? units : slots) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16>, tmRaw, tmB, tmA2, tmB2, tmY, p));
+  FIDM_CHECK_LAUNCH("conv_halo");
+  return 0;
+}
+
+int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
+  FIDM_REQUIRE(conv_halo_supported(a), FIDM_E_SHAPE,
+               "conv (fused GroupNorm operand): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, cout %% 128 == 0");
+  FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
+               "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
+  const bool f16 = a.dtype == FIDM_F16;
+  if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true>(a, st) : launch_conv_halo_t<256, false>(a, st);
+  return f16 ? launch_conv_halo_t<128, true>(a, st) : launch_conv_halo_t<128, false>(a, st);
+}
+
+}  // namespace fidm

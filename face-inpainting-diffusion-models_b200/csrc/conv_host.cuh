@@ -1,0 +1,21 @@
+// Host-side helpers shared by the tensor-core convolution kernels (defined in conv_tc.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fidm {
+
+// NHWC 16-bit tensor [N][H][W][C] (pixel stride ld elements) as a 4-D tiled map with the 128-byte swizzle,
+// box = {64 channels, bw, bh, bn}.
+int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
+                  int f16);
+// Row-major 16-bit matrix [rows][cols] (row stride ld elements) as a 2-D map, box = {64, box_rows}.
+int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows, int f16);
+
+// K1h (conv_halo.cu): 3x3 convolution whose A operand is silu(x * A[n][c] + B[n][c]) of the RAW input, applied
+// while the operand tiles are staged (GroupNorm + SiLU fused into the consumer convolution).
+bool conv_halo_supported(const fidm_conv_args& a);
+int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st);
+
+}  // namespace fidm

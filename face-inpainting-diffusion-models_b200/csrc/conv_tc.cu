@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_host.cuh"
 #include "sm100_primitives.cuh"
 
 namespace fidm {
@@ -570,6 +571,17 @@ extern "C" int fidm_conv_colsum_slots(int32_t height, int32_t width) {
   return 0;
 }
 
+extern "C" int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width, int32_t cin, int32_t cout,
+                                    int32_t ksize, int32_t stride) {
+  fidm_conv_args a = {};
+  a.dtype = FIDM_F16; a.batch = batch; a.height = height; a.width = width;
+  a.cin = cin; a.cout = cout; a.ksize = ksize; a.stride = stride;
+  if (!fidm::conv_halo_supported(a)) return 0;
+  // worth it only when the CTA pairs of the machine are (nearly) all busy: 8 x 16 pixel boxes, two per pair
+  const long long units = (long long)batch * (height / 16) * (width / 16) * (cout / (cout % 256 == 0 ? 256 : 128));
+  return units * 4 >= (long long)(fidm::num_sms() / 2) * 3 ? 1 : 0;
+}
+
 extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
   using namespace fidm;
   FIDM_REQUIRE(a && a->x && a->w && a->y, FIDM_E_BADARG, "conv_tc: null x/w/y");
@@ -585,6 +597,7 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   if (a->residual)
     FIDM_REQUIRE((uintptr_t)a->residual % 16 == 0 && a->ld_res % 8 == 0, FIDM_E_ALIGN, "conv_tc: residual alignment");
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->gn_coef) return launch_conv_halo(*a, st);      // GroupNorm + SiLU of the raw input applied in the operand path
   if (a->cout % 64 != 0 || a->y_nchw_f32) {
     FIDM_REQUIRE(a->y_nchw_f32 && a->cout == 16 && !a->residual, FIDM_E_SHAPE,
                  "conv_tc: cout %d is only supported as the 16-wide fp32-NCHW head", a->cout);

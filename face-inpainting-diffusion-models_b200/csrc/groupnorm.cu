@@ -318,8 +318,53 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnParams p) {
   }
 }
 
+
+// Statistics -> per-(image, channel) affine coefficients of GroupNorm [* (1+scale) + shift] + SiLU, halved
+// (silu(x*A + B) = h + h*tanh(h), h = x*A/2 + B/2).  Same arithmetic as the head of gn_apply_kernel, so a conv that
+// applies the activation in its operand path sees exactly the coefficients the apply pass would have used.
+__global__ void __launch_bounds__(256) gn_coeff_kernel(const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
+  __shared__ float2 mr_s[64];
+  const int n = blockIdx.x;
+  const int hw = a.height * a.width;
+  const int cpg = a.channels / a.groups;
+  if (a.chansum) {
+    const float2* cs = reinterpret_cast<const float2*>(a.chansum) + (long long)n * a.ld_chansum;
+    if (threadIdx.x < a.groups) {
+      double ds = 0.0, dss = 0.0;
+      for (int k = 0; k < cpg; ++k) {
+        const float2 v = cs[threadIdx.x * cpg + k];
+        ds += (double)v.x;
+        dss += (double)v.y;
+      }
+      const double cnt = (double)cpg * hw;
+      const double mean = ds / cnt;
+      double var = dss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mr_s[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+    }
+  } else if (threadIdx.x < a.groups) {
+    const float* mr = reinterpret_cast<const float*>(a.stats) + ((long long)n * a.groups + threadIdx.x) * 2;
+    mr_s[threadIdx.x] = make_float2(mr[0], mr[1]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.channels; c += blockDim.x) {
+    const float2 mr = mr_s[c / cpg];
+    const float ga = a.gamma ? a.gamma[c] : 1.0f;
+    const float be = a.beta ? a.beta[c] : 0.0f;
+    float Ai = mr.y * ga;
+    float Bi = be - mr.x * Ai;
+    if (a.scale_shift) {
+      const float sc = 1.0f + a.scale_shift[(long long)n * a.ld_ss + c];
+      const float sh = a.scale_shift[(long long)n * a.ld_ss + a.channels + c];
+      Ai *= sc;
+      Bi = Bi * sc + sh;
+    }
+    coef[(long long)n * ld_coef + c] = make_float2(0.5f * Ai, 0.5f * Bi);
+  }
+}
+
 template <typename T, typename TY, int VEC>
-static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
+static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = nullptr, int ld_coef = 0) {
   GnParams p;
   p.a = a;
   p.cv = a.channels / VEC;
@@ -356,6 +401,11 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
         p, partials, counters);
     FIDM_CHECK_LAUNCH("groupnorm stats");
   }
+  if (coef) {      // statistics only: the consumer conv applies the activation in its operand path
+    gn_coeff_kernel<<<a.batch, 256, 0, st>>>(a, coef, ld_coef);
+    FIDM_CHECK_LAUNCH("groupnorm coeff");
+    return 0;
+  }
   chunks = plan(it_hw);
   dim3 grid(chunks, a.batch);
   const size_t sm = a.chansum ? sizeof(float2) * (a.channels + a.groups) : 0;
@@ -370,20 +420,20 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st) {
 }
 
 template <typename T, typename TY>
-static int dispatch_vec(const fidm_gn_args& a, cudaStream_t st) {
+static int dispatch_vec(const fidm_gn_args& a, cudaStream_t st, float2* coef = nullptr, int ld_coef = 0) {
   const int cpg = a.channels / a.groups;
   constexpr int MAXV = 16 / sizeof(T);  // 16-byte vectors
   auto aligned = [&](int v) {
     const size_t bytes = sizeof(T) * v;
-    bool ok = (cpg % v == 0) && (a.ld_x % v == 0) && (a.ld_y % v == 0) && ((uintptr_t)a.x % bytes == 0) &&
-              ((uintptr_t)a.y % bytes == 0);
+    bool ok = (cpg % v == 0) && (a.ld_x % v == 0) && ((uintptr_t)a.x % bytes == 0);
+    if (!coef) ok = ok && (a.ld_y % v == 0) && ((uintptr_t)a.y % bytes == 0);
     if (a.y_raw) ok = ok && (a.ld_raw % v == 0) && ((uintptr_t)a.y_raw % bytes == 0);
     return ok;
   };
-  if (MAXV >= 8 && aligned(8)) return launch_gn<T, TY, 8>(a, st);
-  if (aligned(4)) return launch_gn<T, TY, 4>(a, st);
-  if (aligned(2)) return launch_gn<T, TY, 2>(a, st);
-  return launch_gn<T, TY, 1>(a, st);
+  if (MAXV >= 8 && aligned(8)) return launch_gn<T, TY, 8>(a, st, coef, ld_coef);
+  if (aligned(4)) return launch_gn<T, TY, 4>(a, st, coef, ld_coef);
+  if (aligned(2)) return launch_gn<T, TY, 2>(a, st, coef, ld_coef);
+  return launch_gn<T, TY, 1>(a, st, coef, ld_coef);
 }
 
 }  // namespace fidm
@@ -404,6 +454,22 @@ extern "C" int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t str
   if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(*a, (cudaStream_t)stream);
   if (a->dtype == FIDM_F32) return dispatch_vec<float, float>(*a, (cudaStream_t)stream);
   FIDM_REQUIRE(false, FIDM_E_BADARG, "groupnorm: bad dtype %d", a->dtype);
+}
+
+extern "C" int fidm_groupnorm_silu_coeff(const fidm_gn_args* a, float* coef, int32_t ld_coef, fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(a && a->x && coef && (a->stats || a->chansum), FIDM_E_BADARG, "groupnorm coeff: null x/coef/stats");
+  FIDM_REQUIRE(a->batch > 0 && a->height > 0 && a->width > 0 && a->channels > 0, FIDM_E_BADARG, "groupnorm coeff: empty shape");
+  FIDM_REQUIRE(a->groups > 0 && a->groups <= 64 && a->channels % a->groups == 0, FIDM_E_SHAPE,
+               "groupnorm coeff: channels %d not divisible into %d groups", a->channels, a->groups);
+  FIDM_REQUIRE(a->ld_x >= a->channels && ld_coef >= a->channels && !a->skip_norm, FIDM_E_BADARG, "groupnorm coeff: bad ld / skip_norm");
+  if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "groupnorm coeff: ld_ss < 2*channels");
+  fidm_gn_args b = *a;
+  b.resample = FIDM_RESAMPLE_NONE;
+  float2* c2 = reinterpret_cast<float2*>(coef);
+  if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(b, (cudaStream_t)stream, c2, ld_coef);
+  if (a->dtype == FIDM_F32) return dispatch_vec<float, float>(b, (cudaStream_t)stream, c2, ld_coef);
+  FIDM_REQUIRE(false, FIDM_E_BADARG, "groupnorm coeff: bad dtype %d", a->dtype);
 }
 
 namespace fidm {

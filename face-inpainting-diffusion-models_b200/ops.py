@@ -105,14 +105,41 @@ def groupnorm_silu(x, gamma=None, beta=None, *, scale_shift=None, silu=True, res
     return (y, raw) if want_raw else y
 
 
+def groupnorm_silu_coeff(x, gamma=None, beta=None, *, scale_shift=None, groups=32, eps=1e-5, chansum=None):
+    """Statistics only: the halved affine coefficients [N, C, 2] of GroupNorm(+scale/shift)+SiLU, for
+    conv2d(..., gn_coef=coef) which applies the activation while staging its operand tiles."""
+    n, h, w, c, ld = _nhwc(x)
+    coef = torch.empty(n, c, 2, device=x.device, dtype=torch.float32)
+    stats = torch.zeros(L.lib().fidm_groupnorm_workspace_bytes(n, groups) // 8, device=x.device, dtype=torch.float64)
+    a = L.GnArgs()
+    a.dtype, a.y_dtype = L.dtype_code(x.dtype), L.dtype_code(x.dtype)
+    a.batch, a.height, a.width, a.channels, a.groups, a.eps = n, h, w, c, groups, eps
+    a.x, a.ld_x = L.ptr(x), ld
+    a.gamma, a.beta = L.ptr(gamma), L.ptr(beta)
+    if scale_shift is not None:
+        assert scale_shift.dtype == torch.float32 and scale_shift.stride(1) == 1
+        a.scale_shift, a.ld_ss = L.ptr(scale_shift), scale_shift.stride(0)
+    a.silu = 1
+    a.stats = L.ptr(stats)
+    if chansum is not None:
+        a.chansum, a.ld_chansum = L.ptr(chansum), chansum.shape[1]
+    L.check(L.lib().fidm_groupnorm_silu_coeff(C.byref(a), L.ptr(coef), c, L.stream()), "groupnorm_coeff")
+    return coef
+
+
 def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=None, w2=None, out=None,
-           nchw_out_channels=None, impl="auto", want_chansum=False):
-    """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto"."""
+           nchw_out_channels=None, impl="auto", want_chansum=False, gn_coef=None):
+    """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto".
+    gn_coef [N, Cin, 2] (from groupnorm_silu_coeff): x is the raw bf16 stream and the conv operand is
+    silu(GroupNorm(x)), applied inside the kernel; w_krsc's dtype (fp16 | bf16) is the staged operand's dtype."""
     n, h, w, cin, ld = _nhwc(x)
     cout, ks = w_krsc.shape[0], w_krsc.shape[1]
     ho, wo = ((h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1)
     a = L.ConvArgs()
-    a.dtype, a.batch, a.height, a.width = L.dtype_code(x.dtype), n, h, w
+    a.dtype, a.batch, a.height, a.width = L.dtype_code(w_krsc.dtype if gn_coef is not None else x.dtype), n, h, w
+    if gn_coef is not None:
+        assert x.dtype == torch.bfloat16 and gn_coef.dtype == torch.float32 and gn_coef.shape[-1] == 2
+        a.gn_coef, a.ld_gn_coef = L.ptr(gn_coef), gn_coef.stride(0) // 2
     a.cin, a.cout, a.ksize, a.stride = cin, cout, ks, stride
     a.x, a.ld_x, a.w = L.ptr(x), ld, L.ptr(w_krsc)
     if x2 is not None:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FIDM_ABI_VERSION 1
+#define FIDM_ABI_VERSION 2
 
 #define FIDM_F32  0
 #define FIDM_BF16 1
@@ -179,6 +179,11 @@ typedef struct fidm_gn_args {
 } fidm_gn_args;
 int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream);
 int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
+/* Statistics only (same arguments; y / resample / silu ignored): writes the per-(image, channel) affine coefficients of
+ * GroupNorm [* (1+scale) + shift] followed by SiLU, HALVED:  coef[n][c] = (A/2, B/2)  with  A = rstd*gamma*(1+scale),
+ * B = (beta - mean*rstd*gamma)*(1+scale) + shift,  so that silu(x*A + B) = h + h*tanh(h), h = x*coef.x + coef.y.
+ * Consumed by fidm_conv2d_nhwc_bf16(gn_coef = coef): the normalisation pass itself never runs. */
+int fidm_groupnorm_silu_coeff(const fidm_gn_args* a, float* coef, int32_t ld_coef, fidm_stream_t stream);
 /* chansum[n][c0 + c] = sum over the `slots` partial rows of image n of colsum[n][slot][c]  (fixed order) */
 int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, int32_t slots, int32_t channels,
                                  float* chansum, int32_t ld_chansum, int32_t c0, fidm_stream_t stream);
@@ -220,9 +225,19 @@ typedef struct fidm_conv_args {
   void* splitk_ws; int64_t splitk_ws_bytes;  /* optional zero-initialised workspace: lets the tensor-core entry split
                                            the K loop of low-resolution layers over several CTAs (fixed-order fold,
                                            counters are left at zero).  32 MB covers every layer of the UNets here. */
+  const float* gn_coef; int32_t ld_gn_coef;  /* optional (tensor-core entry, fidm_conv_gn_fusable() shapes): x is the RAW
+                                           bf16 stream and the operand is silu(x*A + B) with per-(image, channel)
+                                           coefficients [batch][ld_gn_coef][2] from fidm_groupnorm_silu_coeff -- the
+                                           GroupNorm(+scale/shift)+SiLU in front of this conv (nn.py:151-153,173-176,
+                                           203-207) is applied while the operand tiles are staged; `dtype` is then the
+                                           dtype of w and of the staged operand. */
 } fidm_conv_args;
 /* number of partial rows per image the tensor-core conv writes into `colsum` (0: not supported for this size) */
 int fidm_conv_colsum_slots(int32_t height, int32_t width);
+/* 1 if fidm_conv2d_nhwc_bf16 takes `gn_coef` for this shape (3x3 stride 1, H % 16 == 0, W % 16 == 0, cin % 64 == 0,
+ * cout % 128 == 0) AND the layer is large enough to fill the machine's CTA pairs; 0: run the GroupNorm pass. */
+int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width, int32_t cin, int32_t cout, int32_t ksize,
+                         int32_t stride);
 int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream);
 int fidm_conv2d_nhwc_simt(const fidm_conv_args* a, fidm_stream_t stream);
 

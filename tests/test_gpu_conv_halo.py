@@ -1,0 +1,139 @@
+"""GPU: K1h -- 3x3 convolution with GroupNorm(+scale/shift)+SiLU applied in the operand path
+(nn.py:151-153, 173-176, 203-207) against torch fp32: group_norm -> silu -> conv2d on the same bf16 input."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as Fn
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(B, H, W, Cin, Cout, seed, ld_extra=0):
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    buf = (torch.randn(B, H, W, Cin + ld_extra, device=dev, generator=g) * 1.7 + 0.3).bfloat16()
+    x = buf[..., ld_extra // 2: ld_extra // 2 + Cin] if ld_extra else buf
+    w = torch.randn(Cout, Cin, 3, 3, device=dev, generator=g) / math.sqrt(Cin * 9)
+    b = torch.randn(Cout, device=dev, generator=g)
+    gamma = 1 + 0.2 * torch.randn(Cin, device=dev, generator=g)
+    beta = 0.2 * torch.randn(Cin, device=dev, generator=g)
+    return x, w, b, gamma, beta, g
+
+
+def _act(x, gamma, beta, ss=None):
+    xr = x.float().permute(0, 3, 1, 2)
+    y = Fn.group_norm(xr, 32, gamma, beta, eps=1e-5)
+    if ss is not None:
+        C = xr.shape[1]
+        y = y * (1 + ss[:, :C, None, None]) + ss[:, C:2 * C, None, None]
+    return Fn.silu(y)
+
+
+def _check(y_nhwc, want, what, rel_tol=4e-3):
+    got = y_nhwc.float().permute(0, 3, 1, 2)
+    rel = ((got - want).norm() / want.norm()).item()
+    err = (got - want).abs().max().item()
+    assert rel < rel_tol and err < 8e-2, (what, rel, err)
+
+
+def test_groupnorm_coeff_matches_formula(cuda_lib):
+    from fidm_b200 import ops
+    x, _, _, gamma, beta, g = _mk(3, 16, 16, 128, 128, seed=3, ld_extra=64)
+    ss = torch.randn(3, 2 * 128 + 32, device="cuda", generator=g)[:, 16:16 + 256] * 0.3
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta, scale_shift=ss)
+    xf = x.float().reshape(3, 256, 32, 4)                      # [n, pixel, group, channel-in-group]
+    mean = xf.mean(dim=(1, 3))
+    var = xf.var(dim=(1, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    A = rstd.repeat_interleave(4, 1) * gamma
+    Bc = beta - mean.repeat_interleave(4, 1) * A
+    A2, B2 = A * (1 + ss[:, :128]), Bc * (1 + ss[:, :128]) + ss[:, 128:]
+    assert torch.allclose(coef[..., 0], 0.5 * A2, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(coef[..., 1], 0.5 * B2, rtol=1e-4, atol=2e-5)
+
+
+SHAPES = [
+    (1, 16, 16, 64, 128, 0),        # one CTA pair, one unit
+    (2, 32, 32, 128, 256, 0),
+    (3, 16, 32, 192, 128, 0),       # odd batch, non-square, 3 K slices
+    (1, 64, 64, 256, 512, 0),       # two N blocks of 256
+    (2, 64, 48, 64, 384, 64),       # three N blocks of 128, input is a channel slice of a wider buffer
+    (2, 128, 128, 256, 256, 0),     # more units than CTA pairs: persistent loop, TMEM double buffering
+]
+
+
+@pytest.mark.parametrize("wdtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ld_extra", SHAPES)
+def test_conv_halo_plain(cuda_lib, B, H, W, Cin, Cout, ld_extra, wdtype):
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    assert cuda_lib.fidm_conv_gn_fusable(8, 256, 256, 256, 256, 3, 1) == 1
+    x, w, b, gamma, beta, _ = _mk(B, H, W, Cin, Cout, seed=H + Cin, ld_extra=ld_extra)
+    wq = w.to(wdtype)
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta)
+    y = ops.conv2d(x, ops.repack_weight(wq.float(), wdtype), b, impl="tc", gn_coef=coef)
+    torch.cuda.synchronize()
+    want = Fn.conv2d(_act(x, gamma, beta), wq.float(), b, padding=1)
+    _check(y, want, (B, H, W, Cin, Cout), rel_tol=4e-3 if wdtype == torch.float16 else 8e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,Cin2", [(2, 32, 32, 128, 256, 64), (1, 64, 64, 64, 128, 192),
+                                                 (2, 128, 128, 128, 256, 128)])
+def test_conv_halo_epilogue_skip_and_stats(cuda_lib, B, H, W, Cin, Cout, Cin2):
+    """scale/shift coefficients, bias + timestep row + residual, the fused 1x1 skip source, writes into a channel
+    slice of a concat buffer, and the fused output statistics feeding the next GroupNorm."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda"
+    x, w, b, gamma, beta, g = _mk(B, H, W, Cin, Cout, seed=Cin2 + H)
+    wq = w.half()
+    wk = ops.repack_weight(wq.float(), torch.float16)
+    ss = torch.randn(B, 2 * Cin, device=dev, generator=g) * 0.3
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta, scale_shift=ss)
+    act = _act(x, gamma, beta, ss)
+    row = torch.randn(B, Cout, device=dev, generator=g)
+    res_buf = torch.randn(B, H, W, Cout + 64, device=dev, generator=g).bfloat16()
+    res = res_buf[..., 64:]
+    y = ops.conv2d(x, wk, b, row_add=row, residual=res, impl="tc", gn_coef=coef)
+    want = Fn.conv2d(act, wq.float(), b, padding=1) + row[:, :, None, None] + res.float().permute(0, 3, 1, 2)
+    _check(y, want, "epilogue")
+    # 1x1 skip source as extra K iterations, output into a slice, fused statistics of the output
+    x2 = torch.randn(B, H, W, Cin2 + 64, device=dev, generator=g).bfloat16()[..., 64:]
+    w2 = (torch.randn(Cout, Cin2, 1, 1, device=dev, generator=g) / math.sqrt(Cin2)).bfloat16()
+    out_buf = torch.zeros(B, H, W, Cout + 128, device=dev, dtype=torch.bfloat16)
+    out = out_buf[..., 64:64 + Cout]
+    _, chansum = ops.conv2d(x, wk, b, x2=x2, w2=ops.repack_weight(w2.float()), out=out, impl="tc", gn_coef=coef,
+                            want_chansum=True)
+    want = Fn.conv2d(act, wq.float(), b, padding=1) + Fn.conv2d(x2.float().permute(0, 3, 1, 2), w2.float())
+    _check(out, want, "skip")
+    assert not out_buf[..., :64].any() and not out_buf[..., 64 + Cout:].any()
+    of = out.float()
+    assert torch.allclose(chansum[..., 0], of.sum(dim=(1, 2)), rtol=1e-3, atol=0.5)
+    assert torch.allclose(chansum[..., 1], (of * of).sum(dim=(1, 2)), rtol=1e-3, atol=0.5)
+
+
+def test_conv_halo_matches_unfused_path(cuda_lib):
+    """Same layer through the two-pass path (GroupNorm apply -> fp16 tensor -> K1): the fused operand path must agree
+    to fp16 rounding of the operand."""
+    from fidm_b200 import ops
+    x, w, b, gamma, beta, _ = _mk(2, 64, 64, 128, 256, seed=11)
+    wk = ops.repack_weight(w.half().float(), torch.float16)
+    a = ops.groupnorm_silu(x, gamma, beta, silu=True, out_dtype=torch.float16)
+    y0 = ops.conv2d(a, wk, b, impl="tc").float()
+    y1 = ops.conv2d(x, wk, b, impl="tc", gn_coef=ops.groupnorm_silu_coeff(x, gamma, beta)).float()
+    assert ((y0 - y1).norm() / y0.norm()).item() < 3e-3
+    # bit-reproducible run to run
+    y2 = ops.conv2d(x, wk, b, impl="tc", gn_coef=ops.groupnorm_silu_coeff(x, gamma, beta)).float()
+    assert torch.equal(y1, y2)
+
+
+def test_conv_halo_rejects_unsupported(cuda_lib):
+    from fidm_b200 import ops
+    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    wk = torch.zeros(128, 3, 3, 64, device="cuda", dtype=torch.float16)
+    coef = torch.zeros(1, 64, 2, device="cuda")
+    with pytest.raises(ValueError):
+        ops.conv2d(x, wk, None, impl="tc", gn_coef=coef)
+    assert cuda_lib.fidm_conv_gn_fusable(8, 8, 8, 1024, 1024, 3, 1) == 0
+    assert cuda_lib.fidm_conv_gn_fusable(8, 256, 256, 256, 256, 1, 1) == 0
