@@ -84,6 +84,7 @@ SYMBOLS = {
     "fidm_conv_colsum_slots": (C.c_int, [i32, i32]),
     "fidm_conv_gn_fusable": (C.c_int, [i32, i32, i32, i32, i32, i32, i32]),
     "fidm_conv2d_nhwc_bf16": (C.c_int, [_P(ConvArgs), vp]),
+    "fidm_conv_set_profile_buffer": (C.c_int, [vp]),
     "fidm_conv2d_nhwc_simt": (C.c_int, [_P(ConvArgs), vp]),
     "fidm_attention_qkv_nhwc_bf16": (C.c_int, [_P(AttnArgs), vp]),
     "fidm_attention_qkv_nhwc_simt": (C.c_int, [_P(AttnArgs), vp]),

@@ -21,8 +21,8 @@
 //   * Epilogue = K1's (bias, timestep row, residual, bf16 TMA store into concat slices, fused GroupNorm statistics
 //     of the output).
 //
-// Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-11 transform, 12 weight-ring TMA producer,
-// 13 MMA issuer (+ TMEM owner), 14 halo TMA producer.  Register budgets are rebalanced with setmaxnreg.
+// Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-12 transform, 13 weight-ring TMA producer,
+// 14 MMA issuer (+ TMEM owner), 15 halo TMA producer.  Register budgets are rebalanced with setmaxnreg.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -44,6 +44,7 @@ struct ConvHaloParams {
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
   float* colsum; int colsum_slots; int cout;
+  unsigned long long* prof;   // optional profiling buffer (fidm_conv_set_profile_buffer): [CTA][role][4] cycle counters
 };
 
 namespace halo {
@@ -66,7 +67,6 @@ constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
 constexpr int kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0 && kOffStaging % 1024 == 0, "swizzle-atom alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-constexpr int kVecPerThread = (kHaloPix * 8 + 127) / 128;   // 16-byte vectors of one halo tile per transform thread (12)
 }  // namespace halo
 
 __device__ __forceinline__ uint32_t ld_shared_u32x4(uint32_t addr, uint32_t& y, uint32_t& z, uint32_t& w) {
@@ -77,38 +77,6 @@ __device__ __forceinline__ uint32_t ld_shared_u32x4(uint32_t addr, uint32_t& y, 
 __device__ __forceinline__ void st_shared_u32x4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// release at cluster scope: the generic-proxy writes (made visible to the async proxy by fence.proxy.async) of this
-// CTA must be ordered before the leader's MMA thread observes the arrival.
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(cta)
-      : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("fidm: mbarrier wait (cluster) timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
-
 // silu(x*A + B) of two packed bf16 values -> two packed 16-bit results (fp16 or bf16).
 template <bool OUT_F16>
 __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, float a1, float b1) {
@@ -162,13 +130,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   const int m_tiles = tiles_img * p.B;                   // even (tiles_w is even)
   const int total_units = (m_tiles >> 1) * p.n_blocks;   // (pair of horizontally adjacent boxes) x N block
 
-  if (warp == 12 && lane == 0) {
+  if (warp == 13 && lane == 0) {
     tma_prefetch_desc(&tmRaw);
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     tma_prefetch_desc(&tmY);
   }
-  if (warp == 13) {
+  if (warp == 14) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
       for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
@@ -185,9 +153,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 12 && lane == 0) {
+  // register budgets per warpgroup (512 threads x 128 at launch): epilogue 2 x 160, transform + producers 2 x 96
+  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+
+  if (warp >= 13) {
+    if (warp == 13 && lane == 0) {
       // ================================================================ weight / second-source ring producer
       int stage = 0; uint32_t phase = 0;
       auto acquire = [&](uint32_t bytes_per_cta) {
@@ -218,7 +189,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
           advance();
         }
       }
-    } else if (warp == 14 && lane == 0) {
+    } else if (warp == 15 && lane == 0) {
       // ================================================================ halo producer (this CTA's own 10 x 18 boxes)
       uint32_t g = 0;
       for (int wu = unit; wu < total_units; wu += n_units) {
@@ -233,7 +204,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
           tma_load_4d(&tmRaw, &raw_full[rb], raw_buf + rb * kRawStride, kc * 64, w0 - 1, h0 - 1, n0);
         }
       }
-    } else if (warp == 13 && lane == 0 && cta_rank == 0) {
+    } else if (warp == 14 && lane == 0 && cta_rank == 0) {
       // ================================================================ MMA issuer (leader CTA)
       constexpr uint32_t idesc_bf16 = umma_idesc_bf16(256, BLOCK_N);
       constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(256, BLOCK_N) : idesc_bf16;
@@ -241,17 +212,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t g = 0;
       const uint32_t copy_addr = smem_u32(copy_buf), ring_addr = smem_u32(ring);
+      long long pf_tmem = 0, pf_a = 0, pf_ring = 0, pf_t;
+      const long long pf_start = clock64();
       for (int wu = unit; wu < total_units; wu += n_units) {
+        pf_t = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        pf_tmem += clock64() - pf_t;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         uint32_t accum = 0;
         for (int kc = 0; kc < p.kc1; ++kc, ++g) {
           for (int s = 0; s < 3; ++s) {
-            mbar_wait_cluster(&a_full[s], g & 1u);
+            pf_t = clock64();
+            mbar_wait(&a_full[s], g & 1u);
+            pf_a += clock64() - pf_t;
             tc_fence_after();
             for (int r = 0; r < 3; ++r) {
+              pf_t = clock64();
               mbar_wait(&ring_full[stage], phase);
+              pf_ring += clock64() - pf_t;
               tc_fence_after();
               const uint64_t da = umma_desc_sw128(copy_addr + s * kCopyBytes + r * 1024);
               const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
@@ -286,72 +265,95 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
         umma_commit_2sm(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.prof) {
+        unsigned long long* o = p.prof + 16 * blockIdx.x;
+        o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_tmem; o[2] = pf_a; o[3] = pf_ring;
+      }
     }
   } else if (warp >= 8) {
-    // ==================================================================== transform warps (8-11)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    // ==================================================================== transform warps (8-12, 160 threads)
+    // Thread = (16-byte channel chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8.
+    // Every shared-memory offset below is a per-thread constant plus an immediate: no address arithmetic in the loop.
     const int tt = (int)threadIdx.x - 256;
-    const int j = tt & 7;                 // 16-byte channel chunk (8 channels) of the 64-channel slice
-    const int pl = tt >> 3;               // pixel lane: this thread owns halo pixels pl, pl + 16, ...
+    const int j = tt & 7;
+    const int l20 = tt >> 3;
+    const int x = l20 % kHW, yh = l20 / kHW;
+    const int px0 = yh * kHW + x, px1 = px0 + 2 * kHW;
     const uint32_t raw_addr = smem_u32(raw_buf), copy_addr = smem_u32(copy_buf);
+    // halo pixel px of the TMA box sits at px * 128 with its 16-byte chunks XOR-swizzled by (px & 7); px advances by
+    // 20 per step of i, so the swizzle term alternates between two values (40 % 8 == 0)
+    const uint32_t ro_even = raw_addr + px0 * 128 + ((j ^ (px0 & 7)) << 4);
+    const uint32_t ro_odd = raw_addr + px1 * 128 + ((j ^ (px1 & 7)) << 4);
+    // copy s: halo row y, pixel x - s  ->  row (y * 8 + x - s) of a K-major 128-byte-swizzled tile
+    uint32_t so[3];
+    bool in_copy[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x - s;
+      in_copy[s] = (unsigned)xx < 8u;
+      so[s] = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + ((j ^ (xx & 7)) << 4);
+    }
     uint32_t g = 0;
+    long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
+    const long long pf_start = clock64();
     for (int wu = unit; wu < total_units; wu += n_units) {
       const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
       const int w0 = (m_blk % p.tiles_w) * kTW;
       const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
       const int n0 = m_blk / tiles_img;
       const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+      // The conv zero-pads the ACTIVATED tensor: halo pixels outside the image must be 0 after the activation.
+      // Only the first / last halo row and column of a box can be outside (H % 16 == 0, W % 8 == 0).
+      const bool col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
+      const bool first_out = col_out || (yh == 0 && h0 == 0);                 // i == 0  (halo row yh)
+      const bool last_out = col_out || (yh == 1 && h0 + kTH == p.H);          // i == 8  (halo row 16 + yh)
       for (int kc = 0; kc < p.kc1; ++kc, ++g) {
         float4 c[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A,B) of channels 2q, 2q+1 of this chunk
+        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
         const uint32_t rb = g & 1u;
+        pf_t = clock64();
         mbar_wait(&raw_full[rb], (g >> 1) & 1u);
-        const uint32_t rbase = raw_addr + rb * kRawStride;
-        uint4 v[kVecPerThread];
+        pf_raw += clock64() - pf_t;
+        pf_t = clock64();
+        const uint32_t roff = rb * kRawStride;
+        uint4 v[9];
 #pragma unroll
-        for (int i = 0; i < kVecPerThread; ++i) {
-          const int px = pl + 16 * i;
-          v[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (px < kHaloPix) {
-            const int y = px / kHW, x = px - y * kHW;
-            const bool inside = (unsigned)(w0 - 1 + x) < (unsigned)p.W && (unsigned)(h0 - 1 + y) < (unsigned)p.H;
-            if (inside) {   // the conv zero-pads the ACTIVATED tensor: out-of-image pixels stay 0
-              uint32_t r1, r2, r3;
-              const uint32_t r0 = ld_shared_u32x4(rbase + px * 128 + ((j ^ (px & 7)) << 4), r1, r2, r3);
-              v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
-              v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
-              v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
-              v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
-            }
-          }
+        for (int i = 0; i < 9; ++i) {
+          uint32_t r1, r2, r3;
+          const uint32_t r0 = ld_shared_u32x4(((i & 1) ? ro_odd : ro_even) + roff + (i >> 1) * (4 * kHW * 128), r1, r2, r3);
+          v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+          v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+          v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+          v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+          const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+          if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
         }
+        pf_work += clock64() - pf_t;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          // copy s holds, for halo row y, the pixels x = s .. s + 7 as the 8 rows of one swizzle atom
+          pf_t = clock64();
           mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
-          const uint32_t cbase = copy_addr + s * kCopyBytes;
+          pf_ae += clock64() - pf_t;
+          if (in_copy[s]) {
 #pragma unroll
-          for (int i = 0; i < kVecPerThread; ++i) {
-            const int px = pl + 16 * i;
-            if (px < kHaloPix) {
-              const int y = px / kHW, x = px - y * kHW;
-              const int xx = x - s;
-              if ((unsigned)xx < 8u) st_shared_u32x4(cbase + (y * 8 + xx) * 128 + ((j ^ xx) << 4), v[i]);
-            }
+            for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(7, 128);
+          named_bar_sync(7, 160);
           if (tt == 0) {
             if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the halo tile
-            mbar_arrive_cluster_release(&a_full[s], 0);
+            mbar_arrive_cluster(&a_full[s], 0);
           }
         }
       }
     }
+    if (p.prof && tt == 0) {
+      unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
+      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
+    }
   } else {
     // ==================================================================== epilogue (warps 0-7), as in K1
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int wg = warp >> 2, qw = warp & 3;          // warp (qw) may only touch TMEM lanes [32 qw, 32 qw + 32)
     const int row = qw * 32 + lane;                   // TMEM lane == pixel row of this CTA's box
     const uint32_t lane_sel = (uint32_t)(qw * 32) << 16;
@@ -360,6 +362,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
     const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
     uint8_t* const stage_out = staging + wg * kStagingBytes;
     int acc = 0; uint32_t acc_phase = 0;
+    long long pf_full = 0, pf_t;
+    const long long pf_start = clock64();
     for (int wu = unit; wu < total_units; wu += n_units) {
       const int n_blk = wu % p.n_blocks, m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
       const int w0 = (m_blk % p.tiles_w) * kTW;
@@ -368,7 +372,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
       const int co0 = n_blk * BLOCK_N;
       const long long pix = ((long long)n * p.H + (h0 + hl)) * p.W + (w0 + wl);
 
+      pf_t = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
+      pf_full += clock64() - pf_t;
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
@@ -463,17 +469,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) bulk_wait_group_read<0>();
+    if (p.prof && threadIdx.x == 0) {
+      unsigned long long* o = p.prof + 16 * blockIdx.x + 8;
+      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_full;
+    }
   }
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 13) {
+  if (warp == 14) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------ host
+static unsigned long long* g_prof = nullptr;
+
 bool conv_halo_supported(const fidm_conv_args& a) {
   return a.ksize == 3 && a.stride == 1 && a.height % halo::kTH == 0 && a.width % (2 * halo::kTW) == 0 &&
          a.cin % 64 == 0 && a.cin > 0 && a.cout % 128 == 0 && !a.y_nchw_f32 &&
@@ -494,6 +506,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 2;
+  p.prof = g_prof;
 
   CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY;
   int rc;
@@ -541,3 +554,8 @@ int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
 }
 
 }  // namespace fidm
+
+extern "C" int fidm_conv_set_profile_buffer(uint64_t* device_buffer) {
+  fidm::g_prof = reinterpret_cast<unsigned long long*>(device_buffer);
+  return 0;
+}

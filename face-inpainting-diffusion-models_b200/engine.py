@@ -178,6 +178,8 @@ class Plan:
         self.keep = []
         # fused GroupNorm statistics: per-storage [B, ld, 2] channel sums written by the producing convs
         self.fuse_stats = os.environ.get("FIDM_FUSE_GN_STATS", "1") != "0" and weights.precision == "bf16"
+        # GroupNorm + SiLU applied in the consumer conv's operand path (K1h) where fidm_conv_gn_fusable() says so
+        self.fuse_gn = os.environ.get("FIDM_FUSE_GN_APPLY", "1") != "0"
         self.chansum = {}        # id(storage) -> fp32 [B, ld, 2]
         self.coverage = {}       # id(storage) -> [(c0, channels)]
         self.colsum_scratch = {}  # numel -> fp32 scratch for the per-tile partial rows
@@ -301,13 +303,46 @@ class Plan:
         self.keep.append(a)
         self._op(self.lib.fidm_groupnorm_silu_nhwc, C.byref(a))
 
+    def _fusable(self, name, H, W):
+        """True if conv `name` at HxW can apply its GroupNorm+SiLU input in the operand path (K1h)."""
+        if not (self.fuse_gn and self.w.precision == "bf16"):
+            return False
+        wt, _, cin_pad, cout_pad, ks = self.w.conv[name]
+        return bool(self.lib.fidm_conv_gn_fusable(self.B, H, W, cin_pad, cout_pad, ks, 1))
+
+    def _gn_coeff(self, x, name, scale_shift=None):
+        """Statistics of x -> halved affine coefficients [B, C, 2] for a conv with a fused GroupNorm+SiLU operand."""
+        w = self.w
+        coef = torch.empty(self.B, x.channels, 2, device=w.device, dtype=torch.float32)
+        a = L.GnArgs()
+        a.dtype = a.y_dtype = L.dtype_code(x.storage.dtype)
+        a.batch, a.height, a.width, a.channels, a.groups = self.B, x.H, x.W, x.channels, 32
+        a.eps = 1e-5
+        a.x, a.ld_x = x.ptr, x.ld
+        a.gamma, a.beta = L.ptr(w.vec[name + ".weight"]), L.ptr(w.vec[name + ".bias"])
+        if scale_shift is not None:
+            a.scale_shift = L.ptr(self.emb_all, scale_shift * 4)
+            a.ld_ss = self.emb_all.shape[1]
+        a.silu = 1
+        a.stats = L.ptr(self.stats)
+        if self._covered(x):
+            cs = self.chansum[id(x.storage)]
+            a.chansum, a.ld_chansum = L.ptr(cs, x.c0 * 8), cs.shape[1]
+        self.keep.append((a, coef))
+        self._op(self.lib.fidm_groupnorm_silu_coeff, C.byref(a), L.ptr(coef), x.channels)
+        return coef
+
     def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
-              cout_valid=None, stats=True):
+              cout_valid=None, stats=True, gn_coef=None):
         w = self.w
         wt, bias, cin_pad, cout_pad, ks = w.conv[name]
         assert x.channels == cin_pad, (name, x.channels, cin_pad)
         a = L.ConvArgs()
-        assert x.storage.dtype == wt.dtype, (name, x.storage.dtype, wt.dtype)
+        if gn_coef is None:
+            assert x.storage.dtype == wt.dtype, (name, x.storage.dtype, wt.dtype)
+        else:       # raw bf16 stream in; the kernel stages silu(x*A + B) in the weights' dtype
+            assert x.storage.dtype == torch.bfloat16 and wt.dtype in (torch.float16, torch.bfloat16)
+            a.gn_coef, a.ld_gn_coef = L.ptr(gn_coef), gn_coef.shape[1]
         a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, x.H, x.W
         a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
         a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
@@ -329,7 +364,7 @@ class Plan:
         self.keep.append(a)
         tc_ok = (w.precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
                  (x2 is None or x2.channels % 64 == 0))
-        assert tc_ok or wt.dtype != torch.float16
+        assert tc_ok or (wt.dtype != torch.float16 and gn_coef is None)
         fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
         # Fusing the consumer GroupNorm's statistics into this epilogue pays off where the separate statistics
         # pass is HBM-bound (large tensors) and the epilogue is off the critical path (long K loop); measured
@@ -403,23 +438,33 @@ class Plan:
             H, W, mode = H // 2, W // 2, L.RESAMPLE_DOWN
         else:
             mode = L.RESAMPLE_NONE
-        a1 = self._new(H, W, layer.cin, self._wdtype(n + ".in_layers.2"))
-        xr = self._new(H, W, layer.cin) if mode != L.RESAMPLE_NONE else None
-        self._gn(x, a1, n + ".in_layers.0", silu=True, resample=mode, y_raw=xr)
-        h = self._new(H, W, layer.cout)
         off = w.emb_off[n]
-        self._conv(n + ".in_layers.2", a1, h, row_add=None if self.ssn else off)
-        self._release(a1)
-        a2 = self._new(H, W, layer.cout, self._wdtype(n + ".out_layers.3"))
-        self._gn(h, a2, n + ".out_layers.0", silu=True, scale_shift=off if self.ssn else None)
-        self._release(h)
+        xr = None
+        h = None
+        if mode == L.RESAMPLE_NONE and self._fusable(n + ".in_layers.2", H, W):
+            # GroupNorm + SiLU of x applied inside the conv (K1h): no normalized tensor, no apply pass
+            coef = self._gn_coeff(x, n + ".in_layers.0")
+            h = self._new(H, W, layer.cout)
+            self._conv(n + ".in_layers.2", x, h, row_add=None if self.ssn else off, gn_coef=coef)
+        else:
+            a1 = self._new(H, W, layer.cin, self._wdtype(n + ".in_layers.2"))
+            xr = self._new(H, W, layer.cin) if mode != L.RESAMPLE_NONE else None
+            self._gn(x, a1, n + ".in_layers.0", silu=True, resample=mode, y_raw=xr)
+            h = self._new(H, W, layer.cout)
+            self._conv(n + ".in_layers.2", a1, h, row_add=None if self.ssn else off)
+            self._release(a1)
         y = dst if dst is not None else self._new(H, W, layer.cout)
         xs = xr if xr is not None else x
-        if layer.skip == "identity":
-            self._conv(n + ".out_layers.3", a2, y, residual=xs)
+        skip = dict(residual=xs) if layer.skip == "identity" else dict(x2=xs, name2=n + ".skip_connection")
+        if self._fusable(n + ".out_layers.3", H, W) and (layer.skip == "identity" or layer.cin % 64 == 0):
+            coef = self._gn_coeff(h, n + ".out_layers.0", scale_shift=off if self.ssn else None)
+            self._conv(n + ".out_layers.3", h, y, gn_coef=coef, **skip)
         else:
-            self._conv(n + ".out_layers.3", a2, y, x2=xs, name2=n + ".skip_connection")
-        self._release(a2)
+            a2 = self._new(H, W, layer.cout, self._wdtype(n + ".out_layers.3"))
+            self._gn(h, a2, n + ".out_layers.0", silu=True, scale_shift=off if self.ssn else None)
+            self._conv(n + ".out_layers.3", a2, y, **skip)
+            self._release(a2)
+        self._release(h)
         if xr is not None:
             self._release(xr)
         return y
@@ -512,6 +557,8 @@ class Plan:
         for fn, args in self.ops:
             if fn is self.lib.fidm_groupnorm_silu_nhwc:
                 n += 1 if (args[0]._obj.skip_norm or args[0]._obj.chansum) else 2
+            elif fn is self.lib.fidm_groupnorm_silu_coeff:
+                n += 1 if args[0]._obj.chansum else 2
             else:
                 n += 1
         return n

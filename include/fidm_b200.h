@@ -239,6 +239,11 @@ int fidm_conv_colsum_slots(int32_t height, int32_t width);
 int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width, int32_t cin, int32_t cout, int32_t ksize,
                          int32_t stride);
 int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream);
+/* Profiling hook (NULL disables; default).  With a device buffer of 16 x grid uint64, every CTA of the gn_coef kernel
+ * records SM cycles: [0..3] MMA issuer (total, waiting for a free accumulator, for a transformed operand copy, for
+ * a weight stage), [4..7] transform warps (total, waiting for the halo tile, for a free copy, computing),
+ * [8..9] epilogue (total, waiting for an accumulator). */
+int fidm_conv_set_profile_buffer(uint64_t* device_buffer);
 int fidm_conv2d_nhwc_simt(const fidm_conv_args* a, fidm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
