@@ -354,36 +354,32 @@ def hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S):
 
 
 def dominant_kernel_roofline(ops, dev, pk, B):
-    """conv3x3 256->256 @ 256x256 (31 % of ADM256 FLOPs), timed alone on this stream."""
+    """The dominant layer, conv3x3 256->256 @ 256x256 (31 % of ADM256 FLOPs), as it runs inside the
+    UNet: K1h = GroupNorm+SiLU of the raw input applied in the operand path + tcgen05 implicit GEMM + fused output
+    statistics; timed alone on this stream.  K1 (same layer on a pre-normalized operand) is reported beside it."""
     import math
     Cin = Cout = 256
     H = W = 256
     x = torch.randn(B, H, W, Cin, device=dev).bfloat16()           # 268 MB at B=8: larger than L2
-    w = ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9))
+    x16 = x.half()
+    w16 = ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9), torch.float16)
     b = torch.zeros(Cout, device=dev)
     y = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
-    for _ in range(3):
-        ops.conv2d(x, w, b, out=y, impl="tc")
-    torch.cuda.synchronize()
-    n = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        ops.conv2d(x, w, b, out=y, impl="tc")
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    coef = ops.groupnorm_silu_coeff(x, torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev))
+    ms = _time_launches(lambda: ops.conv2d(x, w16, b, out=y, impl="tc", gn_coef=coef))
+    ms_k1 = _time_launches(lambda: ops.conv2d(x16, w16, b, out=y, impl="tc"))
     flops = 2.0 * B * H * W * Cout * Cin * 9
     ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "conv_tc_kernel<256> (3x3, 256->256, 256x256, batch %d)" % B, "bound": "tensor",
-            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+    return {"kernel": "conv_halo_kernel<256> (GroupNorm+SiLU operand path + 3x3 conv, 256->256, 256x256, batch %d)" % B,
+            "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_src": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": ms,
             "flops_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at batch 8 from the committed
-            # `ncu --set full` capture (profiles/r1_ncu_full_conv_gn.txt): 269.7 MB + 247.5 MB; the algorithmic
+            # `ncu --set full` capture (profiles/r1_ncu_full_conv_halo.txt): 271.2 MB + 239.4 MB; the algorithmic
             # minimum is 268.4 MB in + 268.4 MB out + 1.2 MB of weights
-            "traffic": 517.1e6 * B / 8, "traffic_src": "profiles/r1_ncu_full_conv_gn.txt",
-            "tensor_pipe_active_pct_ncu": 68.2}
+            "traffic": 510.6e6 * B / 8, "traffic_src": "profiles/r1_ncu_full_conv_halo.txt",
+            "tensor_pipe_active_pct_ncu": 83.7,
+            "k1_same_layer_prenormalized_operand": {"ms_per_launch": ms_k1, "achieved": flops / (ms_k1 * 1e-3) / 1e12}}
 
 
 if __name__ == "__main__":

@@ -1,0 +1,24 @@
+"""A few launches of K1h (conv 3x3 256->256 @ 256x256, batch 8, GroupNorm+SiLU in the operand path) for
+`ncu --set full -k regex:conv_halo`."""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import fidm_b200 as F  # noqa: F401
+from fidm_b200 import ops
+
+dev = "cuda:0"
+B, H, W, Cin, Cout = 8, 256, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256
+x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+w = ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9), torch.float16)
+b = torch.zeros(Cout, device=dev)
+y = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
+coef = ops.groupnorm_silu_coeff(x, torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev))
+for _ in range(6):
+    ops.conv2d(x, w, b, out=y, impl="tc", gn_coef=coef, want_chansum=True)
+torch.cuda.synchronize()
+print("ok", float(y.float().abs().mean()))
