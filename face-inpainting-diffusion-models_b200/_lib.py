@@ -78,6 +78,7 @@ SYMBOLS = {
     "fidm_timestep_embedding": (C.c_int, [fp, fp, fp, i32, i32, vp]),
     "fidm_linear_small": (C.c_int, [fp, vp, i32, fp, fp, i32, i32, i32, i32, vp]),
     "fidm_groupnorm_silu_nhwc": (C.c_int, [_P(GnArgs), vp]),
+    "fidm_groupnorm_num_launches": (C.c_int, [_P(GnArgs)]),
     "fidm_groupnorm_workspace_bytes": (C.c_int64, [i32, i32]),
     "fidm_groupnorm_reduce_colsum": (C.c_int, [fp, i32, i32, i32, fp, i32, i32, vp]),
     "fidm_groupnorm_silu_coeff": (C.c_int, [_P(GnArgs), fp, i32, vp]),

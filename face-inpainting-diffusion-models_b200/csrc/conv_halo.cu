@@ -22,7 +22,7 @@
 //     of the output).
 //
 // Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-12 transform, 13 weight-ring TMA producer,
-// 14 MMA issuer (+ TMEM owner), 15 halo TMA producer.  Register budgets are rebalanced with setmaxnreg.
+// 14 MMA issuer (+ TMEM owner).  128 registers per thread suit every role (no setmaxnreg rebalancing needed).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -39,6 +39,7 @@ struct ConvHaloParams {
   int n_blocks;             // Cout / BLOCK_N
   int kc1, cin1;            // Cin / 64, Cin
   int kc2;                  // Cin2 / 64 of the optional 1x1 second source
+  const __nv_bfloat16* x; int ld_x;  // RAW input stream, NHWC, pixel stride ld_x elements
   const float2* coef; int ld_coef;   // [B][ld_coef] (A/2, B/2) per (image, input channel)
   const float* bias;
   const float* row_add; int ld_row_add;
@@ -52,15 +53,11 @@ constexpr int kThreads = 512;
 constexpr int kEpiWarps = 8;
 constexpr int kTW = 8, kTH = 16;                       // output pixel box of one CTA
 constexpr int kHW = kTW + 2, kHH = kTH + 2;            // halo tile
-constexpr int kHaloPix = kHW * kHH;                    // 180
-constexpr int kRawBytes = kHaloPix * 128;              // 23040 (TMA transaction size)
-constexpr int kRawStride = 23 * 1024;                  // buffers stay 1024-byte aligned (swizzle atom)
 constexpr int kCopyBytes = kHH * 1024;                 // [18 rows][8 pixels][128 B]
 constexpr int kRingStageBytes = 16384;                 // one weight half-tile (<= 128 rows x 128 B) or one A2 box
-constexpr int kRingStages = 5;
+constexpr int kRingStages = 8;
 constexpr int kStagingBytes = 128 * 128;
-constexpr int kOffRaw = 0;
-constexpr int kOffCopy = kOffRaw + 2 * kRawStride;
+constexpr int kOffCopy = 0;
 constexpr int kOffRing = kOffCopy + 3 * kCopyBytes;
 constexpr int kOffStaging = kOffRing + kRingStages * kRingStageBytes;
 constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
@@ -96,7 +93,7 @@ __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, f
 
 template <int BLOCK_N, bool OUT_F16>
 __global__ void __launch_bounds__(halo::kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmB,
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
   using namespace halo;
@@ -107,18 +104,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* const raw_buf = smem + kOffRaw;
   uint8_t* const copy_buf = smem + kOffCopy;
   uint8_t* const ring = smem + kOffRing;
   uint8_t* const staging = smem + kOffStaging;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* const raw_full = bars;              // [2]  TMA -> transform
-  uint64_t* const raw_empty = bars + 2;         // [2]  transform -> halo producer
-  uint64_t* const a_full = bars + 4;            // [3]  transform (both CTAs) -> MMA issuer   (leader's copy is used)
-  uint64_t* const a_empty = bars + 7;           // [3]  MMA commit -> transform (multicast to both CTAs)
-  uint64_t* const ring_full = bars + 10;        // [kRingStages]
-  uint64_t* const ring_empty = bars + 10 + kRingStages;
-  uint64_t* const tmem_full = bars + 10 + 2 * kRingStages;    // [2]
+  uint64_t* const a_full = bars;                // [3]  transform (both CTAs) -> MMA issuer   (leader's copy is used)
+  uint64_t* const a_empty = bars + 3;           // [3]  MMA commit -> transform (multicast to both CTAs)
+  uint64_t* const ring_full = bars + 6;         // [kRingStages]
+  uint64_t* const ring_empty = bars + 6 + kRingStages;
+  uint64_t* const tmem_full = bars + 6 + 2 * kRingStages;     // [2]
   uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -131,14 +125,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   const int total_units = (m_tiles >> 1) * p.n_blocks;   // (pair of horizontally adjacent boxes) x N block
 
   if (warp == 13 && lane == 0) {
-    tma_prefetch_desc(&tmRaw);
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     tma_prefetch_desc(&tmY);
   }
   if (warp == 14) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
       for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 2); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
@@ -152,10 +144,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // register budgets per warpgroup (512 threads x 128 at launch): epilogue 2 x 160, transform + producers 2 x 96
-  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
 
   if (warp >= 13) {
     if (warp == 13 && lane == 0) {
@@ -187,21 +175,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
           acquire(kBBytes);
           tma_load_2d_2sm(&tmB2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
           advance();
-        }
-      }
-    } else if (warp == 15 && lane == 0) {
-      // ================================================================ halo producer (this CTA's own 10 x 18 boxes)
-      uint32_t g = 0;
-      for (int wu = unit; wu < total_units; wu += n_units) {
-        const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
-        const int w0 = (m_blk % p.tiles_w) * kTW;
-        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
-        const int n0 = m_blk / tiles_img;
-        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
-          const uint32_t rb = g & 1u;
-          mbar_wait(&raw_empty[rb], ((g >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(&raw_full[rb], kRawBytes);
-          tma_load_4d(&tmRaw, &raw_full[rb], raw_buf + rb * kRawStride, kc * 64, w0 - 1, h0 - 1, n0);
         }
       }
     } else if (warp == 14 && lane == 0 && cta_rank == 0) {
@@ -272,18 +245,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
     }
   } else if (warp >= 8) {
     // ==================================================================== transform warps (8-12, 160 threads)
-    // Thread = (16-byte channel chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8.
-    // Every shared-memory offset below is a per-thread constant plus an immediate: no address arithmetic in the loop.
+    // Thread = (16-byte channel chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8,
+    // of every 64-channel slice: nine 16-byte global loads (prefetched one slice ahead into registers), one
+    // activation pass, and up to three stores per vector.  Shared-memory offsets are per-thread constants + immediates.
     const int tt = (int)threadIdx.x - 256;
     const int j = tt & 7;
     const int l20 = tt >> 3;
     const int x = l20 % kHW, yh = l20 / kHW;
-    const int px0 = yh * kHW + x, px1 = px0 + 2 * kHW;
-    const uint32_t raw_addr = smem_u32(raw_buf), copy_addr = smem_u32(copy_buf);
-    // halo pixel px of the TMA box sits at px * 128 with its 16-byte chunks XOR-swizzled by (px & 7); px advances by
-    // 20 per step of i, so the swizzle term alternates between two values (40 % 8 == 0)
-    const uint32_t ro_even = raw_addr + px0 * 128 + ((j ^ (px0 & 7)) << 4);
-    const uint32_t ro_odd = raw_addr + px1 * 128 + ((j ^ (px1 & 7)) << 4);
+    const uint32_t copy_addr = smem_u32(copy_buf);
     // copy s: halo row y, pixel x - s  ->  row (y * 8 + x - s) of a K-major 128-byte-swizzled tile
     uint32_t so[3];
     bool in_copy[3];
@@ -293,60 +262,80 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
       in_copy[s] = (unsigned)xx < 8u;
       so[s] = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + ((j ^ (xx & 7)) << 4);
     }
+    const long long row2 = 2LL * p.W * p.ld_x;        // two image rows, in elements
+
+    // (tile, slice) cursor of the prefetch stream
+    int n_wu = unit, n_kc = 0;
+    uint4 nxt[9];
+    float4 nc[4];
+    bool n_col_out = false, n_first_out = false, n_last_out = false;
+    int n_img = 0;
+    auto prefetch = [&]() {
+      const int m_blk = (n_wu / p.n_blocks) * 2 + (int)cta_rank;
+      const int w0 = (m_blk % p.tiles_w) * kTW;
+      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+      n_img = m_blk / tiles_img;
+      // The conv zero-pads the ACTIVATED tensor: halo pixels outside the image must be 0 after the activation.
+      // Only the first / last halo row and column of a box can be outside (H % 16 == 0, W % 8 == 0).
+      n_col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
+      n_first_out = n_col_out || (yh == 0 && h0 == 0);                 // i == 0  (halo row yh)
+      n_last_out = n_col_out || (yh == 1 && h0 + kTH == p.H);          // i == 8  (halo row 16 + yh)
+      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n_img * p.ld_coef + n_kc * 64 + j * 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nc[q] = __ldg(cf + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
+      const __nv_bfloat16* gp = p.x + (((long long)n_img * p.H + (h0 - 1 + yh)) * p.W + (w0 - 1 + x)) * p.ld_x +
+                                n_kc * 64 + j * 8;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const bool out = (i == 0) ? n_first_out : (i == 8) ? n_last_out : n_col_out;
+        nxt[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (!out) nxt[i] = __ldg(reinterpret_cast<const uint4*>(gp + i * row2));
+      }
+    };
+    bool have = n_wu < total_units;
+    if (have) prefetch();
     uint32_t g = 0;
     long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
     const long long pf_start = clock64();
-    for (int wu = unit; wu < total_units; wu += n_units) {
-      const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
-      const int w0 = (m_blk % p.tiles_w) * kTW;
-      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
-      const int n0 = m_blk / tiles_img;
-      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
-      // The conv zero-pads the ACTIVATED tensor: halo pixels outside the image must be 0 after the activation.
-      // Only the first / last halo row and column of a box can be outside (H % 16 == 0, W % 8 == 0).
-      const bool col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
-      const bool first_out = col_out || (yh == 0 && h0 == 0);                 // i == 0  (halo row yh)
-      const bool last_out = col_out || (yh == 1 && h0 + kTH == p.H);          // i == 8  (halo row 16 + yh)
-      for (int kc = 0; kc < p.kc1; ++kc, ++g) {
-        float4 c[4];
+    while (have) {
+      // ---- current slice <- prefetched registers
+      uint4 v[9];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
-        const uint32_t rb = g & 1u;
-        pf_t = clock64();
-        mbar_wait(&raw_full[rb], (g >> 1) & 1u);
-        pf_raw += clock64() - pf_t;
-        pf_t = clock64();
-        const uint32_t roff = rb * kRawStride;
-        uint4 v[9];
+      for (int i = 0; i < 9; ++i) v[i] = nxt[i];
+      const bool col_out = n_col_out, first_out = n_first_out, last_out = n_last_out;
+      float4 c[4];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          uint32_t r1, r2, r3;
-          const uint32_t r0 = ld_shared_u32x4(((i & 1) ? ro_odd : ro_even) + roff + (i >> 1) * (4 * kHW * 128), r1, r2, r3);
-          v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
-          v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
-          v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
-          v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
-          const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
-          if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        pf_work += clock64() - pf_t;
+      for (int q = 0; q < 4; ++q) c[q] = nc[q];
+      // ---- advance the cursor and issue the next slice's loads (they land while this slice is processed)
+      if (++n_kc == p.kc1) { n_kc = 0; n_wu += n_units; }
+      have = n_wu < total_units;
+      if (have) prefetch();
+      pf_t = clock64();
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          pf_t = clock64();
-          mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
-          pf_ae += clock64() - pf_t;
-          if (in_copy[s]) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(7, 160);
-          if (tt == 0) {
-            if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the halo tile
-            mbar_arrive_cluster(&a_full[s], 0);
-          }
-        }
+      for (int i = 0; i < 9; ++i) {
+        const uint4 r = v[i];
+        v[i].x = act_pair<OUT_F16>(r.x, c[0].x, c[0].y, c[0].z, c[0].w);
+        v[i].y = act_pair<OUT_F16>(r.y, c[1].x, c[1].y, c[1].z, c[1].w);
+        v[i].z = act_pair<OUT_F16>(r.z, c[2].x, c[2].y, c[2].z, c[2].w);
+        v[i].w = act_pair<OUT_F16>(r.w, c[3].x, c[3].y, c[3].z, c[3].w);
+        const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+        if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
       }
+      pf_work += clock64() - pf_t;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        pf_t = clock64();
+        mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+        pf_ae += clock64() - pf_t;
+        if (in_copy[s]) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(7, 160);
+        if (tt == 0) mbar_arrive_cluster(&a_full[s], 0);
+      }
+      ++g;
     }
     if (p.prof && tt == 0) {
       unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
@@ -501,6 +490,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.n_blocks = a.cout / BLOCK_N;
   p.kc1 = a.cin / 64; p.cin1 = a.cin;
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a.x); p.ld_x = a.ld_x;
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
@@ -508,16 +498,15 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.colsum_slots = p.tiles_w * p.tiles_h * 2;
   p.prof = g_prof;
 
-  CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY;
+  CUtensorMap tmB, tmA2, tmB2, tmY;
   int rc;
-  // the raw stream is bf16; only the element SIZE matters to the copy engine
-  if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHW, kHH, 1, 0))) return rc;
+  FIDM_REQUIRE((uintptr_t)a.x % 16 == 0 && a.ld_x % 8 == 0, FIDM_E_ALIGN, "conv (fused GroupNorm operand): x must be 16-byte aligned");
   if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, OUT_F16 ? 1 : 0))) return rc;
   if (a.x2) {
     if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kTW, kTH, 1, 0))) return rc;
     if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N / 2, 0))) return rc;
   } else {
-    tmA2 = tmRaw; tmB2 = tmB;
+    tmA2 = tmB; tmB2 = tmB;
   }
   if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kTW, kTH, 1, 0))) return rc;
   static bool attr_set = false;
@@ -538,7 +527,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16>, tmRaw, tmB, tmA2, tmB2, tmY, p));
+  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16>, tmB, tmA2, tmB2, tmY, p));
   FIDM_CHECK_LAUNCH("conv_halo");
   return 0;
 }

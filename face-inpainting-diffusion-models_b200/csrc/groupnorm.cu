@@ -10,6 +10,8 @@
 // affine coefficients in registers.  Statistics are accumulated in fp32 per thread, then reduced in
 // double precision in a fixed order (block partials, folded by the last block of each image to finish):
 // no floating-point atomics, so the result is bit-reproducible.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fidm {
@@ -172,6 +174,130 @@ __device__ __forceinline__ float silu_f(float v) {
     return fmaf(h, t, h);
   }
   return v / (1.0f + expf(-v));
+}
+
+// Small (L2-resident) tensors: ONE launch.  A block owns one (image, group): it reads the group's channel slice of every
+// pixel once into registers, reduces (sum, sum of squares) in a fixed tree, and writes the normalized / activated
+// values -- instead of a statistics launch plus an apply launch that reads the tensor twice.  Up to NV 16-byte vectors
+// per thread (NV * blockDim vectors per (image, group)).
+template <typename TY, int NV>
+__global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
+  __shared__ double red[16][2];
+  __shared__ float mr[2];
+  constexpr bool FAST = true;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int hw = a.height * a.width;
+  const int cpg = a.channels / a.groups;
+  const int total = hw * vpp;                           // 16-byte vectors of this (image, group)
+  const int t = threadIdx.x;
+  const bool active = t < stride;                       // stride = largest multiple of vpp <= blockDim: the channel
+  const int jv = t % vpp;                               // chunk (t % vpp) of a thread is the same for all its vectors
+  const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(a.x) + (long long)n * hw * a.ld_x + g * cpg;
+  uint4 v[NV];
+  float s = 0.0f, ss = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = t + k * stride;
+    v[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (active && i < total) v[k] = *reinterpret_cast<const uint4*>(xin + (long long)(i / vpp) * a.ld_x + jv * 8);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float f0 = __uint_as_float(u[e] << 16), f1 = __uint_as_float(u[e] & 0xFFFF0000u);
+      s += f0 + f1;
+      ss = fmaf(f0, f0, ss);
+      ss = fmaf(f1, f1, ss);
+    }
+  }
+  double ds = (double)s, dss = (double)ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  if ((t & 31) == 0) { red[t >> 5][0] = ds; red[t >> 5][1] = dss; }
+  __syncthreads();
+  if (t == 0) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a0 += red[k][0]; a1 += red[k][1]; }
+    const double cnt = (double)cpg * hw;
+    const double mean = a0 / cnt;
+    double var = a1 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mr[0] = (float)mean;
+    mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  if (!active) return;
+  const float meanf = mr[0], rstd = mr[1];
+  const int c0 = g * cpg + jv * 8;
+  float A[8], B[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float ga = a.gamma ? a.gamma[c0 + i] : 1.0f;
+    const float be = a.beta ? a.beta[c0 + i] : 0.0f;
+    float Ai = rstd * ga;
+    float Bi = be - meanf * Ai;
+    if (a.scale_shift) {
+      const float sc = 1.0f + a.scale_shift[(long long)n * a.ld_ss + c0 + i];
+      const float sh = a.scale_shift[(long long)n * a.ld_ss + a.channels + c0 + i];
+      Ai *= sc;
+      Bi = Bi * sc + sh;
+    }
+    A[i] = Ai;
+    B[i] = Bi;
+  }
+  TY* yo = reinterpret_cast<TY*>(a.y) + (long long)n * hw * a.ld_y + c0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = t + k * stride;
+    if (i < total) {
+      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float y0 = fmaf(__uint_as_float(u[e] << 16), A[2 * e], B[2 * e]);
+        const float y1 = fmaf(__uint_as_float(u[e] & 0xFFFF0000u), A[2 * e + 1], B[2 * e + 1]);
+        f[2 * e] = a.silu ? silu_f<FAST>(y0) : y0;
+        f[2 * e + 1] = a.silu ? silu_f<FAST>(y1) : y1;
+      }
+      store_vec<TY, 8>(yo + (long long)(i / vpp) * a.ld_y, f);
+    }
+  }
+}
+
+// bf16 input, no resampling, no fused producer statistics, 16-byte aligned group slices, <= 8 * 512 vectors per
+// (image, group): the one-launch path.  Returns -1 when it does not apply.
+static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_o, int* stride_o, int* per_thread_o) {
+  static const bool enabled = getenv("FIDM_GN_FUSED_SMALL") == nullptr || atoi(getenv("FIDM_GN_FUSED_SMALL")) != 0;
+  const int cpg = a.channels / a.groups;
+  if (!enabled || a.dtype != FIDM_BF16 || (a.y_dtype != FIDM_BF16 && a.y_dtype != FIDM_F16)) return false;
+  if (a.skip_norm || a.chansum || a.resample != FIDM_RESAMPLE_NONE || cpg % 8 != 0) return false;
+  if (a.ld_x % 8 || a.ld_y % 8 || (uintptr_t)a.x % 16 || (uintptr_t)a.y % 16) return false;
+  const int vpp = cpg / 8;
+  const long long total = (long long)a.height * a.width * vpp;
+  const int threads = total >= 512 ? 512 : (int)((total + 31) / 32) * 32;
+  if (threads < vpp) return false;
+  const int stride = (threads / vpp) * vpp;
+  const long long per_thread = (total + stride - 1) / stride;
+  if (per_thread > 8) return false;    // 8 vectors (64 values) per thread stay in registers
+  *vpp_o = vpp; *threads_o = threads; *stride_o = stride; *per_thread_o = (int)per_thread;
+  return true;
+}
+
+template <typename TY>
+static int try_gn_fused_small(const fidm_gn_args& a, cudaStream_t st) {
+  int vpp, threads, stride, per_thread;
+  if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread)) return -1;
+  dim3 grid(a.groups, a.batch);
+  if (per_thread <= 2) gn_fused_small_kernel<TY, 2><<<grid, threads, 0, st>>>(a, vpp, stride);
+  else if (per_thread <= 4) gn_fused_small_kernel<TY, 4><<<grid, threads, 0, st>>>(a, vpp, stride);
+  else gn_fused_small_kernel<TY, 8><<<grid, threads, 0, st>>>(a, vpp, stride);
+  FIDM_CHECK_LAUNCH("groupnorm (fused small)");
+  return 0;
 }
 
 template <typename T, typename TY, int VEC, int RESAMPLE>
@@ -449,9 +575,15 @@ extern "C" int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t str
   if (a->resample == FIDM_RESAMPLE_DOWN)
     FIDM_REQUIRE(a->height % 2 == 0 && a->width % 2 == 0, FIDM_E_SHAPE, "groupnorm: odd size for 2x pooling");
   if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "groupnorm: ld_ss < 2*channels");
-  if (a->dtype == FIDM_BF16 && a->y_dtype == FIDM_F16) return dispatch_vec<__nv_bfloat16, __half>(*a, (cudaStream_t)stream);
+  if (a->dtype == FIDM_BF16 && a->y_dtype == FIDM_F16) {
+    { const int rc = try_gn_fused_small<__half>(*a, (cudaStream_t)stream); if (rc >= 0) return rc; }
+    return dispatch_vec<__nv_bfloat16, __half>(*a, (cudaStream_t)stream);
+  }
   FIDM_REQUIRE(a->y_dtype == a->dtype, FIDM_E_BADARG, "groupnorm: y_dtype %d not supported with dtype %d", a->y_dtype, a->dtype);
-  if (a->dtype == FIDM_BF16) return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(*a, (cudaStream_t)stream);
+  if (a->dtype == FIDM_BF16) {
+    { const int rc = try_gn_fused_small<__nv_bfloat16>(*a, (cudaStream_t)stream); if (rc >= 0) return rc; }
+    return dispatch_vec<__nv_bfloat16, __nv_bfloat16>(*a, (cudaStream_t)stream);
+  }
   if (a->dtype == FIDM_F32) return dispatch_vec<float, float>(*a, (cudaStream_t)stream);
   FIDM_REQUIRE(false, FIDM_E_BADARG, "groupnorm: bad dtype %d", a->dtype);
 }
@@ -518,6 +650,13 @@ extern "C" int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, 
                                                                  reinterpret_cast<float2*>(chansum), ld_chansum, c0);
   FIDM_CHECK_LAUNCH("reduce_colsum");
   return 0;
+}
+
+extern "C" int fidm_groupnorm_num_launches(const fidm_gn_args* a) {
+  int v, t, s, pt;
+  if (!a) return 0;
+  if (a->skip_norm || a->chansum) return 1;
+  return fidm::gn_fused_small_plan(*a, &v, &t, &s, &pt) ? 1 : 2;
 }
 
 extern "C" int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups) {

@@ -211,6 +211,8 @@ class Plan:
                  B, ted, ted, 1)
         self._op(lib.fidm_linear_small, L.ptr(self.emb), L.ptr(w.emb_w), L.F32, L.ptr(w.emb_b), L.ptr(self.emb_all),
                  B, ted, w.emb_total, 1)
+        self.n_time_ops = len(self.ops)      # K5 depends only on t: a parallel branch of the graph (see launch_all)
+        self.first_emb_use = None            # index of the first op that reads emb_all
 
         # ---- concat buffers of the output path (unet.py:170): cat_j = [h | hs.pop()]
         n_in = len(topo.input_blocks)
@@ -258,6 +260,11 @@ class Plan:
     def _op(self, fn, *args):
         self.ops.append((fn, args))
 
+    def _uses_emb(self):
+        """The op about to be appended reads the timestep table (join point of the K5 branch)."""
+        if self.first_emb_use is None:
+            self.first_emb_use = len(self.ops)
+
     def _new(self, H, W, Cn, dtype=None):
         t = self.pool.get(self.B, H, W, Cn, dtype)
         self.coverage.pop(id(t), None)           # new contents: previously fused statistics are stale
@@ -292,6 +299,7 @@ class Plan:
             off = scale_shift
             a.scale_shift = L.ptr(self.emb_all, off * 4)
             a.ld_ss = self.emb_all.shape[1]
+            self._uses_emb()
         a.silu, a.resample, a.skip_norm = int(silu), resample, int(skip_norm)
         a.y, a.ld_y = y.ptr, y.ld
         if y_raw is not None:
@@ -323,6 +331,7 @@ class Plan:
         if scale_shift is not None:
             a.scale_shift = L.ptr(self.emb_all, scale_shift * 4)
             a.ld_ss = self.emb_all.shape[1]
+            self._uses_emb()
         a.silu = 1
         a.stats = L.ptr(self.stats)
         if self._covered(x):
@@ -353,6 +362,7 @@ class Plan:
         if row_add is not None:
             a.row_add = L.ptr(self.emb_all, row_add * 4)
             a.ld_row_add = self.emb_all.shape[1]
+            self._uses_emb()
         if residual is not None:
             a.residual, a.ld_res = residual.ptr, residual.ld
         if nchw_out is not None:
@@ -527,12 +537,28 @@ class Plan:
         L.check(self.lib.fidm_pack_nchw_to_nhwc(a, L.stream()), "pack")
         self.t_in.copy_(timesteps[batch_offset:batch_offset + self.B], non_blocking=True)
 
-    def launch_all(self):
+    def _launch(self, ops):
         st = L.stream()
-        for fn, args in self.ops:
+        for fn, args in ops:
             rc = fn(*args, st)
             if rc != 0:
                 L.check(rc, fn.__name__)
+
+    def launch_all(self, fork_time_path=False):
+        """Launch the schedule on the current stream.  fork_time_path (used under graph capture): the timestep path
+        (K5: embedding + three small Linears, 300 MB of weights) depends only on t, so it runs on a side stream next
+        to the stem convolution and the first statistics pass and joins before its first consumer."""
+        k, j = self.n_time_ops, self.first_emb_use
+        if not fork_time_path or j is None or j <= k:
+            return self._launch(self.ops)
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._launch(self.ops[:k])
+        self._launch(self.ops[k:j])
+        main.wait_stream(side)
+        self._launch(self.ops[j:])
 
     def run(self):
         """Evaluate the UNet on self.x_in / self.t_in into self.out."""
@@ -545,8 +571,9 @@ class Plan:
                 torch.cuda.current_stream().synchronize()
                 self._warm = True
             g = torch.cuda.CUDAGraph()
+            self._side_stream = torch.cuda.Stream()
             with torch.cuda.graph(g):
-                self.launch_all()
+                self.launch_all(fork_time_path=os.environ.get("FIDM_FORK_TIME_PATH", "1") != "0")
             self.graph = g
         self.graph.replay()
         return self.out
@@ -556,7 +583,7 @@ class Plan:
         n = 0
         for fn, args in self.ops:
             if fn is self.lib.fidm_groupnorm_silu_nhwc:
-                n += 1 if (args[0]._obj.skip_norm or args[0]._obj.chansum) else 2
+                n += self.lib.fidm_groupnorm_num_launches(args[0])
             elif fn is self.lib.fidm_groupnorm_silu_coeff:
                 n += 1 if args[0]._obj.chansum else 2
             else:

@@ -178,6 +178,9 @@ typedef struct fidm_gn_args {
                                            of x (from fidm_groupnorm_reduce_colsum): replaces the statistics pass */
 } fidm_gn_args;
 int fidm_groupnorm_silu_nhwc(const fidm_gn_args* a, fidm_stream_t stream);
+/* kernels fidm_groupnorm_silu_nhwc launches for these arguments: 1 (statistics from the producer, plain resample, or a
+ * small L2-resident tensor handled by the one-pass kernel) or 2 (statistics + apply) */
+int fidm_groupnorm_num_launches(const fidm_gn_args* a);
 int64_t fidm_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
 /* Statistics only (same arguments; y / resample / silu ignored): writes the per-(image, channel) affine coefficients of
  * GroupNorm [* (1+scale) + shift] followed by SiLU, HALVED:  coef[n][c] = (A/2, B/2)  with  A = rstd*gamma*(1+scale),
