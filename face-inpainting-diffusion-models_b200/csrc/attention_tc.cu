@@ -30,14 +30,20 @@ constexpr int kAttnThreads = 192;
 constexpr int BQ = 128, BK = 128, HD = 64;
 constexpr int kTileBytes = 128 * 128;     // 128 rows x 64 bf16, 128-byte swizzled
 constexpr int kKvStages = 2;
-// smem: Q | K[2] | V[2] | P (2 x 16 KB, reused as the output staging tile) | barriers
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kKvStages + 2) + 256 + 1024;
+// smem: Q | K[2] | V[2] | P (2 x 16 KB, reused as the output staging tile) | barriers.  112.25 KB: TWO CTAs per SM
+// (with 1 KB of system reserve each), so that one CTA's softmax overlaps the other's MMAs.  No alignment slack: the
+// dynamic shared window of a kernel without static shared memory starts 1024-byte aligned (checked at run time).
+constexpr int kAttnSmem = kTileBytes * (1 + 2 * kKvStages + 2) + 256;
 constexpr int kAttnTmemCols = 256;        // S: columns [0,128), O tile: [128,192)
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {       // the 128-byte swizzle atoms need a 1024-byte aligned base
+    if (threadIdx.x == 0) printf("fidm: attention shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kTileBytes;
   uint8_t* sV = sK + kKvStages * kTileBytes;

@@ -45,6 +45,7 @@ struct ConvHaloParams {
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
   float* colsum; int colsum_slots; int cout;
+  float* y_nchw; int cout_valid;     // BLOCK_N == 16 (the 6-channel head, unet.py:151): fp32 NCHW output of cout_valid channels
   unsigned long long* prof;   // optional profiling buffer (fidm_conv_set_profile_buffer): [CTA][role][4] cycle counters
 };
 
@@ -98,8 +99,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
   using namespace halo;
   constexpr int kBBytes = (BLOCK_N / 2) * 128;           // this CTA's half of one weight tile
-  constexpr int kTmemCols = 2 * BLOCK_N;
-  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert(BLOCK_N == 16 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(kBBytes <= kRingStageBytes, "ring stage too small");
 
   extern __shared__ uint8_t smem_raw[];
@@ -127,7 +128,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
   if (warp == 13 && lane == 0) {
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
-    tma_prefetch_desc(&tmY);
+    if (BLOCK_N >= 64) tma_prefetch_desc(&tmY);
   }
   if (warp == 14) {
     if (lane == 0) {
@@ -366,6 +367,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
       pf_full += clock64() - pf_t;
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
+      if constexpr (BLOCK_N == 16) {
+        // narrow head (out.2: 6 of 16 output channels): fp32 NCHW stores straight from the accumulator
+        uint32_t v16[16];
+        tmem_ld_32x16(t_acc, v16);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        if (wg == 0) {
+          const long long hw = (long long)p.H * p.W;
+          float* o = p.y_nchw + ((long long)n * p.cout_valid) * hw + (long long)(h0 + hl) * p.W + (w0 + wl);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (q < p.cout_valid) {
+              float val = __uint_as_float(v16[q]);
+              if (p.bias) val += __ldg(p.bias + q);
+              if (p.row_add) val += __ldg(p.row_add + (long long)n * p.ld_row_add + q);
+              o[(long long)q * hw] = val;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
         const int cbase = co0 + ch * 64;
@@ -455,9 +478,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
           *dst = make_float2(s1, s2);
         }
       }
+      }  // BLOCK_N >= 64
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (issuer) bulk_wait_group_read<0>();
+    if (BLOCK_N >= 64 && issuer) bulk_wait_group_read<0>();
     if (p.prof && threadIdx.x == 0) {
       unsigned long long* o = p.prof + 16 * blockIdx.x + 8;
       o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_full;
@@ -477,7 +501,8 @@ static unsigned long long* g_prof = nullptr;
 
 bool conv_halo_supported(const fidm_conv_args& a) {
   return a.ksize == 3 && a.stride == 1 && a.height % halo::kTH == 0 && a.width % (2 * halo::kTW) == 0 &&
-         a.cin % 64 == 0 && a.cin > 0 && a.cout % 128 == 0 && !a.y_nchw_f32 &&
+         a.cin % 64 == 0 && a.cin > 0 &&
+         ((a.cout % 128 == 0 && !a.y_nchw_f32) || (a.cout == 16 && a.y_nchw_f32 && !a.x2 && !a.residual && !a.colsum)) &&
          (a.dtype == FIDM_F16 || a.dtype == FIDM_BF16);
 }
 
@@ -496,6 +521,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 2;
+  p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
   p.prof = g_prof;
 
   CUtensorMap tmB, tmA2, tmB2, tmY;
@@ -508,7 +534,11 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   } else {
     tmA2 = tmB; tmB2 = tmB;
   }
-  if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kTW, kTH, 1, 0))) return rc;
+  if (BLOCK_N >= 64) {
+    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kTW, kTH, 1, 0))) return rc;
+  } else {
+    tmY = tmB;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     FIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, OUT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -534,10 +564,12 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
 
 int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
   FIDM_REQUIRE(conv_halo_supported(a), FIDM_E_SHAPE,
-               "conv (fused GroupNorm operand): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, cout %% 128 == 0");
+               "conv (fused GroupNorm operand): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, cout %% 128 == 0 "
+               "(or the 16-wide fp32-NCHW head)");
   FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
   const bool f16 = a.dtype == FIDM_F16;
+  if (a.cout == 16) return f16 ? launch_conv_halo_t<16, true>(a, st) : launch_conv_halo_t<16, false>(a, st);
   if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true>(a, st) : launch_conv_halo_t<256, false>(a, st);
   return f16 ? launch_conv_halo_t<128, true>(a, st) : launch_conv_halo_t<128, false>(a, st);
 }

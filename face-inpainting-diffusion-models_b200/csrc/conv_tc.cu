@@ -576,9 +576,11 @@ extern "C" int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width
   fidm_conv_args a = {};
   a.dtype = FIDM_F16; a.batch = batch; a.height = height; a.width = width;
   a.cin = cin; a.cout = cout; a.ksize = ksize; a.stride = stride;
+  a.y_nchw_f32 = cout == 16;        // the 16-wide variant is the fp32-NCHW head
   if (!fidm::conv_halo_supported(a)) return 0;
   // worth it only when the CTA pairs of the machine are (nearly) all busy: 8 x 16 pixel boxes, two per pair
-  const long long units = (long long)batch * (height / 16) * (width / 16) * (cout / (cout % 256 == 0 ? 256 : 128));
+  const long long units = (long long)batch * (height / 16) * (width / 16) *
+                          (cout == 16 ? 1 : cout / (cout % 256 == 0 ? 256 : 128));
   return units * 4 >= (long long)(fidm::num_sms() / 2) * 3 ? 1 : 0;
 }
 

@@ -248,9 +248,13 @@ class Plan:
                 dst = self._new(self.H, self.W, blk.cout)
             x = self._block(blk, full, dst)
         # ---- head: out = conv3x3(SiLU(GN(h)))  (unet.py:148-152,173)
-        a = self._new(x.H, x.W, x.channels, self._wdtype("out.2"))
-        self._gn(x, a, "out.0", silu=True)
-        self._conv("out.2", a, None, nchw_out=self.out, cout_valid=topo.out_channels)
+        if self._fusable("out.2", x.H, x.W):
+            coef = self._gn_coeff(x, "out.0")
+            self._conv("out.2", x, None, nchw_out=self.out, cout_valid=topo.out_channels, gn_coef=coef)
+        else:
+            a = self._new(x.H, x.W, x.channels, self._wdtype("out.2"))
+            self._gn(x, a, "out.0", silu=True)
+            self._conv("out.2", a, None, nchw_out=self.out, cout_valid=topo.out_channels)
 
         self.graph = None
         self.use_graph = use_graph

@@ -128,6 +128,24 @@ def test_conv_halo_matches_unfused_path(cuda_lib):
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin", [(2, 64, 64, 64), (1, 256, 256, 128), (3, 16, 32, 256)])
+def test_conv_halo_head_nchw_f32(cuda_lib, B, H, W, Cin):
+    """out = conv3x3(SiLU(GN(h))) with Cout 6 padded to 16 and fp32 NCHW output (unet.py:148-152), GroupNorm fused."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x, w, b, gamma, beta, _ = _mk(B, H, W, Cin, 6, seed=Cin + W)
+    wq = w.half()
+    wk = ops.repack_weight(wq.float(), torch.float16, cout_pad=16)
+    b16 = torch.zeros(16, device="cuda")
+    b16[:6] = b
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta)
+    y = ops.conv2d(x, wk, b16, nchw_out_channels=6, impl="tc", gn_coef=coef)
+    want = Fn.conv2d(_act(x, gamma, beta), wq.float(), b, padding=1)
+    assert y.shape == want.shape
+    rel = ((y - want).norm() / want.norm()).item()
+    assert rel < 3e-3, rel
+
+
 def test_conv_halo_rejects_unsupported(cuda_lib):
     from fidm_b200 import ops
     x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
