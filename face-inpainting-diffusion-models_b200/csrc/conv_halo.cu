@@ -44,6 +44,7 @@ struct ConvHaloParams {
   const float* bias;
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
+  int res_half;             // residual is stored at HALF resolution (x_upd of an up ResBlock, nn.py:194): read (h/2, w/2)
   float* colsum; int colsum_slots; int cout;
   float* y_nchw; int cout_valid;     // BLOCK_N == 16 (the 6-channel head, unet.py:151): fp32 NCHW output of cout_valid channels
   unsigned long long* prof;   // optional profiling buffer (fidm_conv_set_profile_buffer): [CTA][role][4] cycle counters
@@ -92,7 +93,7 @@ __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, f
   return *reinterpret_cast<const uint32_t*>(&o);
 }
 
-template <int BLOCK_N, bool OUT_F16>
+template <int BLOCK_N, bool OUT_F16, bool UP>
 __global__ void __launch_bounds__(halo::kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -246,6 +247,121 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
     }
   } else if (warp >= 8) {
     // ==================================================================== transform warps (8-12, 160 threads)
+    if constexpr (UP) {
+    // Up ResBlock (nn.py:190-195): the operand is nearest-2x-upsample(silu(GN(x))) of the HALF-resolution raw stream.
+    // The 10 x 18 halo of the upsampled image covers a 6 x 10 box of source pixels; thread = (chunk j, source column
+    // lx, row phase lyq) owns the source pixels (lx, lyq + 3i), i = 0..3, activates each ONCE and stores it to the up to
+    // 2 x 2 halo positions it covers (x in {2lx-1, 2lx}, y in {2ly-1, 2ly}) of each shifted copy.
+    const int tt = (int)threadIdx.x - 256;
+    const int j = tt & 7;
+    const int l20 = tt >> 3;
+    const int lx = l20 % 6, lyq = l20 / 6;
+    const bool lane_on = l20 < 18;
+    const uint32_t copy_addr = smem_u32(copy_buf);
+    const int Hs = p.H >> 1, Ws = p.W >> 1;
+    // store bases for (halo column xk in {2lx-1, 2lx}) x (copy s): halo row 2*lyq (the row 2*lyq - 1 is 1024 B below)
+    uint32_t sb[2][3];
+    bool sv[2][3];
+#pragma unroll
+    for (int xk = 0; xk < 2; ++xk) {
+      const int x = 2 * lx - 1 + xk;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x - s;
+        sv[xk][s] = lane_on && (unsigned)x < (unsigned)kHW && (unsigned)xx < 8u;
+        sb[xk][s] = copy_addr + s * kCopyBytes + (2 * lyq) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
+      }
+    }
+    const long long row3 = 3LL * Ws * p.ld_x;          // three source rows, in elements
+
+    int n_wu = unit, n_kc = 0;
+    uint4 nxt[4];
+    float4 nc[4];
+    int n_img = 0;
+    auto prefetch = [&]() {
+      const int m_blk = (n_wu / p.n_blocks) * 2 + (int)cta_rank;
+      const int w0 = (m_blk % p.tiles_w) * kTW;
+      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+      n_img = m_blk / tiles_img;
+      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n_img * p.ld_coef + n_kc * 64 + j * 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nc[q] = __ldg(cf + q);
+      const int lw = (w0 >> 1) - 1 + lx, lh = (h0 >> 1) - 1 + lyq;
+      const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
+      const __nv_bfloat16* gp = p.x + (((long long)n_img * Hs + lh) * Ws + lw) * p.ld_x + n_kc * 64 + j * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // source row lyq + 3i <= 9; rows / columns outside the image stay 0 AFTER the activation (zero padding)
+        const bool ok = col_ok && (lyq + 3 * i <= 9) && (unsigned)(lh + 3 * i) < (unsigned)Hs;
+        nxt[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) nxt[i] = __ldg(reinterpret_cast<const uint4*>(gp + i * row3));
+      }
+    };
+    // which of its source pixels are inside the image is recomputed for the CURRENT slice from saved tile origins
+    bool have = n_wu < total_units;
+    int c_w0 = 0, c_h0 = 0;
+    auto origin = [&](int wu, int& w0, int& h0) {
+      const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+      w0 = (m_blk % p.tiles_w) * kTW;
+      h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+    };
+    if (have) { origin(n_wu, c_w0, c_h0); prefetch(); }
+    uint32_t g = 0;
+    long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
+    const long long pf_start = clock64();
+    while (have) {
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = nxt[i];
+      float4 c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = nc[q];
+      const int lw = (c_w0 >> 1) - 1 + lx, lh = (c_h0 >> 1) - 1 + lyq;
+      const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
+      if (++n_kc == p.kc1) { n_kc = 0; n_wu += n_units; }
+      have = n_wu < total_units;
+      if (have) { origin(n_wu, c_w0, c_h0); prefetch(); }
+      pf_t = clock64();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 r = v[i];
+        v[i].x = act_pair<OUT_F16>(r.x, c[0].x, c[0].y, c[0].z, c[0].w);
+        v[i].y = act_pair<OUT_F16>(r.y, c[1].x, c[1].y, c[1].z, c[1].w);
+        v[i].z = act_pair<OUT_F16>(r.z, c[2].x, c[2].y, c[2].z, c[2].w);
+        v[i].w = act_pair<OUT_F16>(r.w, c[3].x, c[3].y, c[3].z, c[3].w);
+        const bool ok = col_ok && (unsigned)(lh + 3 * i) < (unsigned)Hs;
+        if (!ok) v[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      pf_work += clock64() - pf_t;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        pf_t = clock64();
+        mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+        pf_ae += clock64() - pf_t;
+#pragma unroll
+        for (int xk = 0; xk < 2; ++xk) {
+          if (sv[xk][s]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ly = lyq + 3 * i;                       // source row of the box, 0..9
+              if (ly <= 9) {
+                if (ly >= 1) st_shared_u32x4(sb[xk][s] - 1024 + i * 6144, v[i]);    // halo row 2 ly - 1
+                if (ly <= 8) st_shared_u32x4(sb[xk][s] + i * 6144, v[i]);           // halo row 2 ly
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(7, 160);
+        if (tt == 0) mbar_arrive_cluster(&a_full[s], 0);
+      }
+      ++g;
+    }
+    if (p.prof && tt == 0) {
+      unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
+      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
+    }
+    } else {
     // Thread = (16-byte channel chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8,
     // of every 64-channel slice: nine 16-byte global loads (prefetched one slice ahead into registers), one
     // activation pass, and up to three stores per vector.  Shared-memory offsets are per-thread constants + immediates.
@@ -342,6 +458,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
       unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
       o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
     }
+    }  // !UP
   } else {
     // ==================================================================== epilogue (warps 0-7), as in K1
     const int wg = warp >> 2, qw = warp & 3;          // warp (qw) may only touch TMEM lanes [32 qw, 32 qw + 32)
@@ -360,7 +477,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
       const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
       const int n = m_blk / tiles_img;
       const int co0 = n_blk * BLOCK_N;
-      const long long pix = ((long long)n * p.H + (h0 + hl)) * p.W + (w0 + wl);
+      const long long pix = p.res_half ? ((long long)n * (p.H >> 1) + ((h0 + hl) >> 1)) * (p.W >> 1) + ((w0 + wl) >> 1)
+                                       : ((long long)n * p.H + (h0 + hl)) * p.W + (w0 + wl);      // residual pixel
 
       pf_t = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -506,7 +624,7 @@ bool conv_halo_supported(const fidm_conv_args& a) {
          (a.dtype == FIDM_F16 || a.dtype == FIDM_BF16);
 }
 
-template <int BLOCK_N, bool OUT_F16>
+template <int BLOCK_N, bool OUT_F16, bool UP>
 static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   using namespace halo;
   ConvHaloParams p;
@@ -519,6 +637,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
+  p.res_half = a.residual_half_res;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 2;
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
@@ -541,7 +660,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    FIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, OUT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, OUT_F16, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int units = (p.tiles_w * p.tiles_h * p.B / 2) * p.n_blocks;
@@ -557,7 +676,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16>, tmB, tmA2, tmB2, tmY, p));
+  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16, UP>, tmB, tmA2, tmB2, tmY, p));
   FIDM_CHECK_LAUNCH("conv_halo");
   return 0;
 }
@@ -569,9 +688,14 @@ int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
   FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
   const bool f16 = a.dtype == FIDM_F16;
-  if (a.cout == 16) return f16 ? launch_conv_halo_t<16, true>(a, st) : launch_conv_halo_t<16, false>(a, st);
-  if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true>(a, st) : launch_conv_halo_t<256, false>(a, st);
-  return f16 ? launch_conv_halo_t<128, true>(a, st) : launch_conv_halo_t<128, false>(a, st);
+  if (a.x_half_res) {
+    FIDM_REQUIRE(a.cout != 16, FIDM_E_SHAPE, "conv (fused GroupNorm operand): the head variant does not upsample");
+    if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true, true>(a, st) : launch_conv_halo_t<256, false, true>(a, st);
+    return f16 ? launch_conv_halo_t<128, true, true>(a, st) : launch_conv_halo_t<128, false, true>(a, st);
+  }
+  if (a.cout == 16) return f16 ? launch_conv_halo_t<16, true, false>(a, st) : launch_conv_halo_t<16, false, false>(a, st);
+  if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true, false>(a, st) : launch_conv_halo_t<256, false, false>(a, st);
+  return f16 ? launch_conv_halo_t<128, true, false>(a, st) : launch_conv_halo_t<128, false, false>(a, st);
 }
 
 }  // namespace fidm

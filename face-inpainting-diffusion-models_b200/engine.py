@@ -180,6 +180,7 @@ class Plan:
         self.fuse_stats = os.environ.get("FIDM_FUSE_GN_STATS", "1") != "0" and weights.precision == "bf16"
         # GroupNorm + SiLU applied in the consumer conv's operand path (K1h) where fidm_conv_gn_fusable() says so
         self.fuse_gn = os.environ.get("FIDM_FUSE_GN_APPLY", "1") != "0"
+        self.fuse_up = os.environ.get("FIDM_FUSE_UPSAMPLE", "1") != "0"
         self.chansum = {}        # id(storage) -> fp32 [B, ld, 2]
         self.coverage = {}       # id(storage) -> [(c0, channels)]
         self.colsum_scratch = {}  # numel -> fp32 scratch for the per-tile partial rows
@@ -346,7 +347,7 @@ class Plan:
         return coef
 
     def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
-              cout_valid=None, stats=True, gn_coef=None):
+              cout_valid=None, stats=True, gn_coef=None, x_half=False, residual_half=False):
         w = self.w
         wt, bias, cin_pad, cout_pad, ks = w.conv[name]
         assert x.channels == cin_pad, (name, x.channels, cin_pad)
@@ -356,7 +357,11 @@ class Plan:
         else:       # raw bf16 stream in; the kernel stages silu(x*A + B) in the weights' dtype
             assert x.storage.dtype == torch.bfloat16 and wt.dtype in (torch.float16, torch.bfloat16)
             a.gn_coef, a.ld_gn_coef = L.ptr(gn_coef), gn_coef.shape[1]
-        a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, x.H, x.W
+        # x_half (K1h only): x is the half-resolution raw stream of an `up` ResBlock; the conv runs at 2H x 2W
+        Ho, Wo = (2 * x.H, 2 * x.W) if x_half else (x.H, x.W)
+        assert not (x_half or residual_half) or gn_coef is not None
+        a.x_half_res, a.residual_half_res = int(x_half), int(residual_half)
+        a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, Ho, Wo
         a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
         a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
         if x2 is not None:
@@ -384,9 +389,9 @@ class Plan:
         # pass is HBM-bound (large tensors) and the epilogue is off the critical path (long K loop); measured
         # on B200: 128^2 and larger, K >= 1152.  Small tensors keep the (L2-resident) statistics kernel.
         k_total = ks * ks * cin_pad + (x2.channels if x2 is not None else 0)
-        slots = self.lib.fidm_conv_colsum_slots(x.H, x.W) if (
+        slots = self.lib.fidm_conv_colsum_slots(Ho, Wo) if (
             tc_ok and nchw_out is None and stats and self.fuse_stats and cout_pad % 64 == 0 and
-            x.H * x.W >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
+            Ho * Wo >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
         if slots > 0:
             n = self.B * slots * cout_pad * 2
             if n not in self.colsum_scratch:
@@ -455,11 +460,24 @@ class Plan:
         off = w.emb_off[n]
         xr = None
         h = None
+        fuse_up = (mode == L.RESAMPLE_UP and layer.skip == "identity" and self.fuse_up and
+                   self._fusable(n + ".in_layers.2", H, W) and self._fusable(n + ".out_layers.3", H, W))
         if mode == L.RESAMPLE_NONE and self._fusable(n + ".in_layers.2", H, W):
             # GroupNorm + SiLU of x applied inside the conv (K1h): no normalized tensor, no apply pass
             coef = self._gn_coeff(x, n + ".in_layers.0")
             h = self._new(H, W, layer.cout)
             self._conv(n + ".in_layers.2", x, h, row_add=None if self.ssn else off, gn_coef=coef)
+        elif fuse_up:
+            # `up` ResBlock: GroupNorm + SiLU + nearest 2x upsample of the half-resolution x inside the conv, and
+            # x_upd (nn.py:194) read at (h/2, w/2) by the second conv's epilogue: no upsampled tensor exists
+            coef = self._gn_coeff(x, n + ".in_layers.0")
+            h = self._new(H, W, layer.cout)
+            self._conv(n + ".in_layers.2", x, h, row_add=None if self.ssn else off, gn_coef=coef, x_half=True)
+            y = dst if dst is not None else self._new(H, W, layer.cout)
+            coef = self._gn_coeff(h, n + ".out_layers.0", scale_shift=off if self.ssn else None)
+            self._conv(n + ".out_layers.3", h, y, gn_coef=coef, residual=x, residual_half=True)
+            self._release(h)
+            return y
         else:
             a1 = self._new(H, W, layer.cin, self._wdtype(n + ".in_layers.2"))
             xr = self._new(H, W, layer.cin) if mode != L.RESAMPLE_NONE else None

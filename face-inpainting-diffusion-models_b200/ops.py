@@ -128,15 +128,19 @@ def groupnorm_silu_coeff(x, gamma=None, beta=None, *, scale_shift=None, groups=3
 
 
 def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=None, w2=None, out=None,
-           nchw_out_channels=None, impl="auto", want_chansum=False, gn_coef=None):
+           nchw_out_channels=None, impl="auto", want_chansum=False, gn_coef=None, x_half_res=False,
+           residual_half_res=False):
     """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto".
     gn_coef [N, Cin, 2] (from groupnorm_silu_coeff): x is the raw bf16 stream and the conv operand is
     silu(GroupNorm(x)), applied inside the kernel; w_krsc's dtype (fp16 | bf16) is the staged operand's dtype."""
     n, h, w, cin, ld = _nhwc(x)
+    if x_half_res:            # x is the half-resolution source of an `up` ResBlock: the conv runs at 2h x 2w
+        h, w = 2 * h, 2 * w
     cout, ks = w_krsc.shape[0], w_krsc.shape[1]
     ho, wo = ((h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1)
     a = L.ConvArgs()
     a.dtype, a.batch, a.height, a.width = L.dtype_code(w_krsc.dtype if gn_coef is not None else x.dtype), n, h, w
+    a.x_half_res, a.residual_half_res = int(x_half_res), int(residual_half_res)
     if gn_coef is not None:
         assert x.dtype == torch.bfloat16 and gn_coef.dtype == torch.float32 and gn_coef.shape[-1] == 2
         a.gn_coef, a.ld_gn_coef = L.ptr(gn_coef), gn_coef.stride(0) // 2

@@ -234,6 +234,12 @@ typedef struct fidm_conv_args {
                                            GroupNorm(+scale/shift)+SiLU in front of this conv (nn.py:151-153,173-176,
                                            203-207) is applied while the operand tiles are staged; `dtype` is then the
                                            dtype of w and of the staged operand. */
+  int32_t x_half_res;                   /* with gn_coef: x is [batch][height/2][width/2] and the operand is the nearest
+                                           2x upsample of silu(x*A + B) -- in_layers of an `up` ResBlock (nn.py:190-195:
+                                           GroupNorm, SiLU, Upsample, conv) with no upsampled tensor in memory;
+                                           height/width are the OUTPUT size */
+  int32_t residual_half_res;            /* with gn_coef: residual is [batch][height/2][width/2] and is read at
+                                           (h/2, w/2) -- x_upd of an `up` ResBlock (nn.py:194,212) */
 } fidm_conv_args;
 /* number of partial rows per image the tensor-core conv writes into `colsum` (0: not supported for this size) */
 int fidm_conv_colsum_slots(int32_t height, int32_t width);

@@ -146,6 +146,34 @@ def test_conv_halo_head_nchw_f32(cuda_lib, B, H, W, Cin):
     assert rel < 3e-3, rel
 
 
+@pytest.mark.parametrize("B,Hs,Ws,C,Cout", [(2, 16, 16, 128, 128), (1, 32, 64, 256, 256), (3, 8, 16, 64, 256),
+                                            (2, 64, 64, 256, 256)])
+def test_conv_halo_up_resblock(cuda_lib, B, Hs, Ws, C, Cout):
+    """`up` ResBlock (nn.py:190-212): conv1(upsample(silu(GN(x)))) with x at half resolution, then
+    conv2(silu(GN(h))) + upsample(x): the upsampled tensors never exist in memory."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x, w, b, gamma, beta, g = _mk(B, Hs, Ws, C, Cout, seed=Hs + C)
+    wq = w.half()
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta)
+    h = ops.conv2d(x, ops.repack_weight(wq.float(), torch.float16), b, impl="tc", gn_coef=coef, x_half_res=True)
+    assert h.shape == (B, 2 * Hs, 2 * Ws, Cout)
+    act_up = Fn.interpolate(_act(x, gamma, beta), scale_factor=2, mode="nearest")
+    want_h = Fn.conv2d(act_up, wq.float(), b, padding=1)
+    _check(h, want_h, "up conv1")
+    if Cout == C:
+        # second conv: identity skip = upsample(x), read at (h/2, w/2) by the epilogue
+        g2 = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+        b2 = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+        w2 = (torch.randn(Cout, Cout, 3, 3, device="cuda", generator=g) / math.sqrt(Cout * 9)).half()
+        coef2 = ops.groupnorm_silu_coeff(h, g2, b2)
+        y = ops.conv2d(h, ops.repack_weight(w2.float(), torch.float16), None, impl="tc", gn_coef=coef2, residual=x,
+                       residual_half_res=True)
+        want = Fn.conv2d(_act(h, g2, b2), w2.float(), None, padding=1) + \
+            Fn.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+        _check(y, want, "up conv2 + x_upd")
+
+
 def test_conv_halo_rejects_unsupported(cuda_lib):
     from fidm_b200 import ops
     x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
