@@ -76,7 +76,9 @@ __device__ __forceinline__ uint32_t ld_shared_u32x4(uint32_t addr, uint32_t& y, 
 __device__ __forceinline__ void st_shared_u32x4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// silu(x*A + B) of two packed bf16 values -> two packed 16-bit results (fp16 or bf16).
+// silu(x*A + B) of two packed bf16 values -> two packed 16-bit results (fp16 or bf16).  h = x*A/2 + B/2, then
+// silu = h + h*tanh(h): one MUFU op per value.  (tanh.approx.f16x2 was tried: ptxas splits it into two MUFU.TANH.F16,
+// so it saves no MUFU issue slots and only costs accuracy.)
 template <bool OUT_F16>
 __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, float a1, float b1) {
   const float h0 = fmaf(__uint_as_float(raw << 16), a0, b0);
@@ -415,29 +417,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
     long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
     const long long pf_start = clock64();
     while (have) {
-      // ---- current slice <- prefetched registers
+      // ---- activate the current slice (raw values and coefficients were prefetched into registers) ...
+      pf_t = clock64();
       uint4 v[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) v[i] = nxt[i];
-      const bool col_out = n_col_out, first_out = n_first_out, last_out = n_last_out;
-      float4 c[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = nc[q];
-      // ---- advance the cursor and issue the next slice's loads (they land while this slice is processed)
+      for (int i = 0; i < 9; ++i) {
+        const uint4 r = nxt[i];
+        v[i].x = act_pair<OUT_F16>(r.x, nc[0].x, nc[0].y, nc[0].z, nc[0].w);
+        v[i].y = act_pair<OUT_F16>(r.y, nc[1].x, nc[1].y, nc[1].z, nc[1].w);
+        v[i].z = act_pair<OUT_F16>(r.z, nc[2].x, nc[2].y, nc[2].z, nc[2].w);
+        v[i].w = act_pair<OUT_F16>(r.w, nc[3].x, nc[3].y, nc[3].z, nc[3].w);
+        const bool out = (i == 0) ? n_first_out : (i == 8) ? n_last_out : n_col_out;
+        if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      // ---- ... then advance the cursor and issue the next slice's loads into the registers just freed; they land
+      // while the three copies are written and consumed.  (An additional L2 prefetch stream running two slices ahead
+      // was measured and made the UNet 4 % slower: it competes with the weight stream for the L2 -> SM path.)
       if (++n_kc == p.kc1) { n_kc = 0; n_wu += n_units; }
       have = n_wu < total_units;
       if (have) prefetch();
-      pf_t = clock64();
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const uint4 r = v[i];
-        v[i].x = act_pair<OUT_F16>(r.x, c[0].x, c[0].y, c[0].z, c[0].w);
-        v[i].y = act_pair<OUT_F16>(r.y, c[1].x, c[1].y, c[1].z, c[1].w);
-        v[i].z = act_pair<OUT_F16>(r.z, c[2].x, c[2].y, c[2].z, c[2].w);
-        v[i].w = act_pair<OUT_F16>(r.w, c[3].x, c[3].y, c[3].z, c[3].w);
-        const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
-        if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
       pf_work += clock64() - pf_t;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
