@@ -509,7 +509,7 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
     return (npix + p.pix_per_blk - 1) / p.pix_per_blk;
   };
   int chunks;
-  if (!a.skip_norm && !a.chansum && (long long)hw * (a.channels / a.groups) <= 64 * 64 * 64) {
+  if (!a.skip_norm && !a.chansum && (long long)hw * (a.channels / a.groups) <= 32768) {    // <= 64 KB per (image, group) block
     gn_stats_direct_kernel<T, VEC><<<dim3(a.groups, a.batch), 256, 0, st>>>(p);
     FIDM_CHECK_LAUNCH("groupnorm stats (direct)");
   } else if (!a.skip_norm && !a.chansum) {

@@ -389,6 +389,8 @@ class Plan:
         # pass is HBM-bound (large tensors) and the epilogue is off the critical path (long K loop); measured
         # on B200: 128^2 and larger, K >= 1152.  Small tensors keep the (L2-resident) statistics kernel.
         k_total = ks * ks * cin_pad + (x2.channels if x2 is not None else 0)
+        if name == "input_blocks.0.0" and os.environ.get("FIDM_STEM_STATS", "1") != "0":
+            k_total = 1152      # the stem output feeds TWO GroupNorms (first ResBlock, last skip concat): fuse its statistics
         slots = self.lib.fidm_conv_colsum_slots(Ho, Wo) if (
             tc_ok and nchw_out is None and stats and self.fuse_stats and cout_pad % 64 == 0 and
             Ho * Wo >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
