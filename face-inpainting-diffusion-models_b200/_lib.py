@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfidm_b200.so")
+# FIDM_LIB_PATH: A/B experiments against an older build of the library (symbols it lacks are skipped)
+LIB_PATH = os.environ.get("FIDM_LIB_PATH") or os.path.join(_HERE, "libfidm_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 COEF_COLS = 20
@@ -109,6 +110,8 @@ def lib():
                 "(`python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("FIDM_LIB_PATH") and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
         if handle.fidm_abi_version() != 2:

@@ -22,7 +22,7 @@
 //     of the output).
 //
 // Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-12 transform, 13 weight-ring TMA producer,
-// 14 MMA issuer (+ TMEM owner).  128 registers per thread suit every role (no setmaxnreg rebalancing needed).
+// 14 MMA issuer (+ TMEM owner), 15 halo TMA producer.  128 registers per thread suit every role.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -39,7 +39,6 @@ struct ConvHaloParams {
   int n_blocks;             // Cout / BLOCK_N
   int kc1, cin1;            // Cin / 64, Cin
   int kc2;                  // Cin2 / 64 of the optional 1x1 second source
-  const __nv_bfloat16* x; int ld_x;  // RAW input stream, NHWC, pixel stride ld_x elements
   const float2* coef; int ld_coef;   // [B][ld_coef] (A/2, B/2) per (image, input channel)
   const float* bias;
   const float* row_add; int ld_row_add;
@@ -55,11 +54,17 @@ constexpr int kThreads = 512;
 constexpr int kEpiWarps = 8;
 constexpr int kTW = 8, kTH = 16;                       // output pixel box of one CTA
 constexpr int kHW = kTW + 2, kHH = kTH + 2;            // halo tile
+constexpr int kHaloPix = kHW * kHH;                    // 180
+constexpr int kRawBytes = kHaloPix * 128;              // 23040: TMA transaction of one halo tile (64-channel slice)
+constexpr int kUpW = 6, kUpH = 10;                     // source box of the halo under a nearest 2x upsample
+constexpr int kRawBytesUp = kUpW * kUpH * 128;         // 7680
+constexpr int kRawStride = 23 * 1024;                  // buffers stay 1024-byte aligned (swizzle atom)
 constexpr int kCopyBytes = kHH * 1024;                 // [18 rows][8 pixels][128 B]
 constexpr int kRingStageBytes = 16384;                 // one weight half-tile (<= 128 rows x 128 B) or one A2 box
-constexpr int kRingStages = 8;
+constexpr int kRingStages = 5;
 constexpr int kStagingBytes = 128 * 128;
-constexpr int kOffCopy = 0;
+constexpr int kOffRaw = 0;
+constexpr int kOffCopy = kOffRaw + 2 * kRawStride;
 constexpr int kOffRing = kOffCopy + 3 * kCopyBytes;
 constexpr int kOffStaging = kOffRing + kRingStages * kRingStageBytes;
 constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
@@ -97,7 +102,7 @@ __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, f
 
 template <int BLOCK_N, bool OUT_F16, bool UP>
 __global__ void __launch_bounds__(halo::kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
   using namespace halo;
@@ -108,15 +113,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* const raw_buf = smem + kOffRaw;
   uint8_t* const copy_buf = smem + kOffCopy;
   uint8_t* const ring = smem + kOffRing;
   uint8_t* const staging = smem + kOffStaging;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* const a_full = bars;                // [3]  transform (both CTAs) -> MMA issuer   (leader's copy is used)
-  uint64_t* const a_empty = bars + 3;           // [3]  MMA commit -> transform (multicast to both CTAs)
-  uint64_t* const ring_full = bars + 6;         // [kRingStages]
-  uint64_t* const ring_empty = bars + 6 + kRingStages;
-  uint64_t* const tmem_full = bars + 6 + 2 * kRingStages;     // [2]
+  uint64_t* const raw_full = bars;              // [2]  TMA -> transform
+  uint64_t* const raw_empty = bars + 2;         // [2]  transform -> halo producer
+  uint64_t* const a_full = bars + 4;            // [3]  transform (both CTAs) -> MMA issuer   (leader's copy is used)
+  uint64_t* const a_empty = bars + 7;           // [3]  MMA commit -> transform (multicast to both CTAs)
+  uint64_t* const ring_full = bars + 10;        // [kRingStages]
+  uint64_t* const ring_empty = bars + 10 + kRingStages;
+  uint64_t* const tmem_full = bars + 10 + 2 * kRingStages;    // [2]
   uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -129,12 +137,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
   const int total_units = (m_tiles >> 1) * p.n_blocks;   // (pair of horizontally adjacent boxes) x N block
 
   if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmRaw);
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     if (BLOCK_N >= 64) tma_prefetch_desc(&tmY);
   }
   if (warp == 14) {
     if (lane == 0) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
       for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 2); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
@@ -179,6 +189,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
           acquire(kBBytes);
           tma_load_2d_2sm(&tmB2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
           advance();
+        }
+      }
+    } else if (warp == 15 && lane == 0) {
+      // ================================================================ halo producer: this CTA's own 10 x 18 boxes of the
+      // raw stream (6 x 10 boxes of the half-resolution stream under UP); out-of-image pixels are zero-filled
+      uint32_t g = 0;
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+        const int w0 = (m_blk % p.tiles_w) * kTW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+        const int n0 = m_blk / tiles_img;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          const uint32_t rb = g & 1u;
+          mbar_wait(&raw_empty[rb], ((g >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&raw_full[rb], UP ? kRawBytesUp : kRawBytes);
+          if (UP) tma_load_4d(&tmRaw, &raw_full[rb], raw_buf + rb * kRawStride, kc * 64, (w0 >> 1) - 1, (h0 >> 1) - 1, n0);
+          else tma_load_4d(&tmRaw, &raw_full[rb], raw_buf + rb * kRawStride, kc * 64, w0 - 1, h0 - 1, n0);
         }
       }
     } else if (warp == 14 && lane == 0 && cta_rank == 0) {
@@ -249,214 +276,176 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmB,
     }
   } else if (warp >= 8) {
     // ==================================================================== transform warps (8-12, 160 threads)
-    if constexpr (UP) {
-    // Up ResBlock (nn.py:190-195): the operand is nearest-2x-upsample(silu(GN(x))) of the HALF-resolution raw stream.
-    // The 10 x 18 halo of the upsampled image covers a 6 x 10 box of source pixels; thread = (chunk j, source column
-    // lx, row phase lyq) owns the source pixels (lx, lyq + 3i), i = 0..3, activates each ONCE and stores it to the up to
-    // 2 x 2 halo positions it covers (x in {2lx-1, 2lx}, y in {2ly-1, 2ly}) of each shifted copy.
     const int tt = (int)threadIdx.x - 256;
-    const int j = tt & 7;
+    const int j = tt & 7;                      // 16-byte channel chunk (8 channels) of the 64-channel slice
     const int l20 = tt >> 3;
-    const int lx = l20 % 6, lyq = l20 / 6;
-    const bool lane_on = l20 < 18;
-    const uint32_t copy_addr = smem_u32(copy_buf);
-    const int Hs = p.H >> 1, Ws = p.W >> 1;
-    // store bases for (halo column xk in {2lx-1, 2lx}) x (copy s): halo row 2*lyq (the row 2*lyq - 1 is 1024 B below)
-    uint32_t sb[2][3];
-    bool sv[2][3];
-#pragma unroll
-    for (int xk = 0; xk < 2; ++xk) {
-      const int x = 2 * lx - 1 + xk;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int xx = x - s;
-        sv[xk][s] = lane_on && (unsigned)x < (unsigned)kHW && (unsigned)xx < 8u;
-        sb[xk][s] = copy_addr + s * kCopyBytes + (2 * lyq) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
-      }
-    }
-    const long long row3 = 3LL * Ws * p.ld_x;          // three source rows, in elements
-
-    int n_wu = unit, n_kc = 0;
-    uint4 nxt[4];
-    float4 nc[4];
-    int n_img = 0;
-    auto prefetch = [&]() {
-      const int m_blk = (n_wu / p.n_blocks) * 2 + (int)cta_rank;
-      const int w0 = (m_blk % p.tiles_w) * kTW;
-      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
-      n_img = m_blk / tiles_img;
-      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n_img * p.ld_coef + n_kc * 64 + j * 8);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) nc[q] = __ldg(cf + q);
-      const int lw = (w0 >> 1) - 1 + lx, lh = (h0 >> 1) - 1 + lyq;
-      const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
-      const __nv_bfloat16* gp = p.x + (((long long)n_img * Hs + lh) * Ws + lw) * p.ld_x + n_kc * 64 + j * 8;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // source row lyq + 3i <= 9; rows / columns outside the image stay 0 AFTER the activation (zero padding)
-        const bool ok = col_ok && (lyq + 3 * i <= 9) && (unsigned)(lh + 3 * i) < (unsigned)Hs;
-        nxt[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) nxt[i] = __ldg(reinterpret_cast<const uint4*>(gp + i * row3));
-      }
-    };
-    // which of its source pixels are inside the image is recomputed for the CURRENT slice from saved tile origins
-    bool have = n_wu < total_units;
-    int c_w0 = 0, c_h0 = 0;
-    auto origin = [&](int wu, int& w0, int& h0) {
-      const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
-      w0 = (m_blk % p.tiles_w) * kTW;
-      h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
-    };
-    if (have) { origin(n_wu, c_w0, c_h0); prefetch(); }
+    const uint32_t raw_addr = smem_u32(raw_buf), copy_addr = smem_u32(copy_buf);
     uint32_t g = 0;
     long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
     const long long pf_start = clock64();
-    while (have) {
-      uint4 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = nxt[i];
-      float4 c[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = nc[q];
-      const int lw = (c_w0 >> 1) - 1 + lx, lh = (c_h0 >> 1) - 1 + lyq;
-      const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
-      if (++n_kc == p.kc1) { n_kc = 0; n_wu += n_units; }
-      have = n_wu < total_units;
-      if (have) { origin(n_wu, c_w0, c_h0); prefetch(); }
-      pf_t = clock64();
+    if constexpr (UP) {
+      // Up ResBlock (nn.py:190-195): the operand is nearest-2x-upsample(silu(GN(x))) of the HALF-resolution raw stream.
+      // The 10 x 18 halo of the upsampled image covers a 6 x 10 box of source pixels; thread = (chunk j, source column
+      // lx, row phase lyq) owns the source pixels (lx, lyq + 3i), i = 0..3, activates each ONCE and stores it to the
+      // up to 2 x 2 halo positions it covers (x in {2lx-1, 2lx}, y in {2ly-1, 2ly}) of each shifted copy.
+      const int lx = l20 % kUpW, lyq = l20 / kUpW;
+      const bool lane_on = l20 < 3 * kUpW;
+      const int Hs = p.H >> 1, Ws = p.W >> 1;
+      // source pixel q = ly * 6 + lx of the TMA box sits at q * 128, 16-byte chunks XOR-swizzled by (q & 7)
+      uint32_t ro[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint4 r = v[i];
-        v[i].x = act_pair<OUT_F16>(r.x, c[0].x, c[0].y, c[0].z, c[0].w);
-        v[i].y = act_pair<OUT_F16>(r.y, c[1].x, c[1].y, c[1].z, c[1].w);
-        v[i].z = act_pair<OUT_F16>(r.z, c[2].x, c[2].y, c[2].z, c[2].w);
-        v[i].w = act_pair<OUT_F16>(r.w, c[3].x, c[3].y, c[3].z, c[3].w);
-        const bool ok = col_ok && (unsigned)(lh + 3 * i) < (unsigned)Hs;
-        if (!ok) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        const int q = (lyq + 3 * i) * kUpW + lx;
+        ro[i] = raw_addr + q * 128 + ((j ^ (q & 7)) << 4);
       }
-      pf_work += clock64() - pf_t;
+      // store bases for (halo column x in {2lx-1, 2lx}) x (copy s), halo row 2*lyq (row 2*lyq - 1 is 1024 B below)
+      uint32_t sb[2][3];
+      bool sv[2][3];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        pf_t = clock64();
-        mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
-        pf_ae += clock64() - pf_t;
+      for (int xk = 0; xk < 2; ++xk) {
+        const int x = 2 * lx - 1 + xk;
 #pragma unroll
-        for (int xk = 0; xk < 2; ++xk) {
-          if (sv[xk][s]) {
+        for (int s = 0; s < 3; ++s) {
+          const int xx = x - s;
+          sv[xk][s] = lane_on && (unsigned)x < (unsigned)kHW && (unsigned)xx < 8u;
+          sb[xk][s] = copy_addr + s * kCopyBytes + (2 * lyq) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
+        }
+      }
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+        const int w0 = (m_blk % p.tiles_w) * kTW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+        const int n0 = m_blk / tiles_img;
+        const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+        // zero padding applies AFTER the activation: source pixels outside the image stay 0
+        const int lw = (w0 >> 1) - 1 + lx, lh = (h0 >> 1) - 1 + lyq;
+        const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          float4 c[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ly = lyq + 3 * i;                       // source row of the box, 0..9
-              if (ly <= 9) {
-                if (ly >= 1) st_shared_u32x4(sb[xk][s] - 1024 + i * 6144, v[i]);    // halo row 2 ly - 1
-                if (ly <= 8) st_shared_u32x4(sb[xk][s] + i * 6144, v[i]);           // halo row 2 ly
+          for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);
+          const uint32_t rb = g & 1u;
+          pf_t = clock64();
+          mbar_wait(&raw_full[rb], (g >> 1) & 1u);
+          pf_raw += clock64() - pf_t;
+          pf_t = clock64();
+          const uint32_t roff = rb * kRawStride;
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (col_ok && lyq + 3 * i < kUpH && (unsigned)(lh + 3 * i) < (unsigned)Hs) {
+              uint32_t r1, r2, r3;
+              const uint32_t r0 = ld_shared_u32x4(ro[i] + roff, r1, r2, r3);
+              v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+              v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+              v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+              v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+            }
+          }
+          pf_work += clock64() - pf_t;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            pf_t = clock64();
+            mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+            pf_ae += clock64() - pf_t;
+#pragma unroll
+            for (int xk = 0; xk < 2; ++xk) {
+              if (sv[xk][s]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int ly = lyq + 3 * i;                       // source row of the box, 0..9
+                  if (ly < kUpH) {
+                    if (ly >= 1) st_shared_u32x4(sb[xk][s] - 1024 + i * 6144, v[i]);    // halo row 2 ly - 1
+                    if (ly <= 8) st_shared_u32x4(sb[xk][s] + i * 6144, v[i]);           // halo row 2 ly
+                  }
+                }
               }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(7, 160);
+            if (tt == 0) {
+              if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the source box
+              mbar_arrive_cluster(&a_full[s], 0);
             }
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(7, 160);
-        if (tt == 0) mbar_arrive_cluster(&a_full[s], 0);
       }
-      ++g;
-    }
-    if (p.prof && tt == 0) {
-      unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
-      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
-    }
     } else {
-    // Thread = (16-byte channel chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8,
-    // of every 64-channel slice: nine 16-byte global loads (prefetched one slice ahead into registers), one
-    // activation pass, and up to three stores per vector.  Shared-memory offsets are per-thread constants + immediates.
-    const int tt = (int)threadIdx.x - 256;
-    const int j = tt & 7;
-    const int l20 = tt >> 3;
-    const int x = l20 % kHW, yh = l20 / kHW;
-    const uint32_t copy_addr = smem_u32(copy_buf);
-    // copy s: halo row y, pixel x - s  ->  row (y * 8 + x - s) of a K-major 128-byte-swizzled tile
-    uint32_t so[3];
-    bool in_copy[3];
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int xx = x - s;
-      in_copy[s] = (unsigned)xx < 8u;
-      so[s] = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + ((j ^ (xx & 7)) << 4);
-    }
-    const long long row2 = 2LL * p.W * p.ld_x;        // two image rows, in elements
-
-    // (tile, slice) cursor of the prefetch stream
-    int n_wu = unit, n_kc = 0;
-    uint4 nxt[9];
-    float4 nc[4];
-    bool n_col_out = false, n_first_out = false, n_last_out = false;
-    int n_img = 0;
-    auto prefetch = [&]() {
-      const int m_blk = (n_wu / p.n_blocks) * 2 + (int)cta_rank;
-      const int w0 = (m_blk % p.tiles_w) * kTW;
-      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
-      n_img = m_blk / tiles_img;
-      // The conv zero-pads the ACTIVATED tensor: halo pixels outside the image must be 0 after the activation.
-      // Only the first / last halo row and column of a box can be outside (H % 16 == 0, W % 8 == 0).
-      n_col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
-      n_first_out = n_col_out || (yh == 0 && h0 == 0);                 // i == 0  (halo row yh)
-      n_last_out = n_col_out || (yh == 1 && h0 + kTH == p.H);          // i == 8  (halo row 16 + yh)
-      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n_img * p.ld_coef + n_kc * 64 + j * 8);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) nc[q] = __ldg(cf + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
-      const __nv_bfloat16* gp = p.x + (((long long)n_img * p.H + (h0 - 1 + yh)) * p.W + (w0 - 1 + x)) * p.ld_x +
-                                n_kc * 64 + j * 8;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const bool out = (i == 0) ? n_first_out : (i == 8) ? n_last_out : n_col_out;
-        nxt[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (!out) nxt[i] = __ldg(reinterpret_cast<const uint4*>(gp + i * row2));
-      }
-    };
-    bool have = n_wu < total_units;
-    if (have) prefetch();
-    uint32_t g = 0;
-    long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t;
-    const long long pf_start = clock64();
-    while (have) {
-      // ---- activate the current slice (raw values and coefficients were prefetched into registers) ...
-      pf_t = clock64();
-      uint4 v[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const uint4 r = nxt[i];
-        v[i].x = act_pair<OUT_F16>(r.x, nc[0].x, nc[0].y, nc[0].z, nc[0].w);
-        v[i].y = act_pair<OUT_F16>(r.y, nc[1].x, nc[1].y, nc[1].z, nc[1].w);
-        v[i].z = act_pair<OUT_F16>(r.z, nc[2].x, nc[2].y, nc[2].z, nc[2].w);
-        v[i].w = act_pair<OUT_F16>(r.w, nc[3].x, nc[3].y, nc[3].z, nc[3].w);
-        const bool out = (i == 0) ? n_first_out : (i == 8) ? n_last_out : n_col_out;
-        if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      // ---- ... then advance the cursor and issue the next slice's loads into the registers just freed; they land
-      // while the three copies are written and consumed.  (An additional L2 prefetch stream running two slices ahead
-      // was measured and made the UNet 4 % slower: it competes with the weight stream for the L2 -> SM path.)
-      if (++n_kc == p.kc1) { n_kc = 0; n_wu += n_units; }
-      have = n_wu < total_units;
-      if (have) prefetch();
-      pf_work += clock64() - pf_t;
+      // Thread = (chunk j, halo column x, row parity yh); it owns the halo pixels (x, yh + 2i), i = 0..8.  Every
+      // shared-memory offset below is a per-thread constant plus an immediate: no address arithmetic in the loop.
+      const int x = l20 % kHW, yh = l20 / kHW;
+      const int px0 = yh * kHW + x, px1 = px0 + 2 * kHW;
+      // halo pixel px of the TMA box sits at px * 128 with its 16-byte chunks XOR-swizzled by (px & 7); px advances
+      // by 20 per step of i, so the swizzle term alternates between two values (40 % 8 == 0)
+      const uint32_t ro_even = raw_addr + px0 * 128 + ((j ^ (px0 & 7)) << 4);
+      const uint32_t ro_odd = raw_addr + px1 * 128 + ((j ^ (px1 & 7)) << 4);
+      // copy s: halo row y, pixel x - s  ->  row (y * 8 + x - s) of a K-major 128-byte-swizzled tile
+      uint32_t so[3];
+      bool in_copy[3];
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        pf_t = clock64();
-        mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
-        pf_ae += clock64() - pf_t;
-        if (in_copy[s]) {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(7, 160);
-        if (tt == 0) mbar_arrive_cluster(&a_full[s], 0);
+        const int xx = x - s;
+        in_copy[s] = (unsigned)xx < 8u;
+        so[s] = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + ((j ^ (xx & 7)) << 4);
       }
-      ++g;
+      for (int wu = unit; wu < total_units; wu += n_units) {
+        const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
+        const int w0 = (m_blk % p.tiles_w) * kTW;
+        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
+        const int n0 = m_blk / tiles_img;
+        const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+        // The conv zero-pads the ACTIVATED tensor: halo pixels outside the image must be 0 after the activation.
+        // Only the first / last halo row and column of a box can be outside (H % 16 == 0, W % 8 == 0).
+        const bool col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
+        const bool first_out = col_out || (yh == 0 && h0 == 0);                 // i == 0  (halo row yh)
+        const bool last_out = col_out || (yh == 1 && h0 + kTH == p.H);          // i == 8  (halo row 16 + yh)
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          float4 c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
+          const uint32_t rb = g & 1u;
+          pf_t = clock64();
+          mbar_wait(&raw_full[rb], (g >> 1) & 1u);
+          pf_raw += clock64() - pf_t;
+          pf_t = clock64();
+          const uint32_t roff = rb * kRawStride;
+          uint4 v[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            uint32_t r1, r2, r3;
+            const uint32_t r0 = ld_shared_u32x4(((i & 1) ? ro_odd : ro_even) + roff + (i >> 1) * (4 * kHW * 128), r1, r2, r3);
+            v[i].x = act_pair<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+            v[i].y = act_pair<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+            v[i].z = act_pair<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+            v[i].w = act_pair<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+            const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+            if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          pf_work += clock64() - pf_t;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            pf_t = clock64();
+            mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+            pf_ae += clock64() - pf_t;
+            if (in_copy[s]) {
+#pragma unroll
+              for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(7, 160);
+            if (tt == 0) {
+              if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the halo tile
+              mbar_arrive_cluster(&a_full[s], 0);
+            }
+          }
+        }
+      }
     }
     if (p.prof && tt == 0) {
       unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
       o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
     }
-    }  // !UP
   } else {
     // ==================================================================== epilogue (warps 0-7), as in K1
     const int wg = warp >> 2, qw = warp & 3;          // warp (qw) may only touch TMEM lanes [32 qw, 32 qw + 32)
@@ -631,7 +620,6 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.n_blocks = a.cout / BLOCK_N;
   p.kc1 = a.cin / 64; p.cin1 = a.cin;
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
-  p.x = reinterpret_cast<const __nv_bfloat16*>(a.x); p.ld_x = a.ld_x;
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
@@ -641,9 +629,14 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
   p.prof = g_prof;
 
-  CUtensorMap tmB, tmA2, tmB2, tmY;
+  CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY;
   int rc;
-  FIDM_REQUIRE((uintptr_t)a.x % 16 == 0 && a.ld_x % 8 == 0, FIDM_E_ALIGN, "conv (fused GroupNorm operand): x must be 16-byte aligned");
+  // the raw stream is bf16; only the element SIZE matters to the copy engine
+  if (UP) {
+    if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width / 2, a.height / 2, a.batch, a.ld_x, kUpW, kUpH, 1, 0))) return rc;
+  } else {
+    if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHW, kHH, 1, 0))) return rc;
+  }
   if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, OUT_F16 ? 1 : 0))) return rc;
   if (a.x2) {
     if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kTW, kTH, 1, 0))) return rc;
@@ -674,7 +667,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16, UP>, tmB, tmA2, tmB2, tmY, p));
+  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16, UP>, tmRaw, tmB, tmA2, tmB2, tmY, p));
   FIDM_CHECK_LAUNCH("conv_halo");
   return 0;
 }
