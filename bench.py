@@ -180,6 +180,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the JSON line must be the only thing on stdout: NCCL_DEBUG=VERSION (set on some boxes) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     F._lib.check(F._lib.lib().fidm_device_supported(local), "device")
 
