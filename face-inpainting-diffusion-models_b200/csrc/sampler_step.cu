@@ -38,19 +38,31 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
       t_inj = (a.mode == FIDM_STEP_INJECT_ONLY) ? t_upd : t_upd - 1;
     }
 
-    float xs[VEC];
+    // Every load of this element is issued up front (one memory round trip instead of two dependent ones), and only
+    // what the mode needs is read: the variance channels are skipped when neither the DDPM update nor a caller wants
+    // the log-variance (DDIM: 64 B per pixel instead of 76).
+    const bool upd = a.mode != FIDM_STEP_INJECT_ONLY, inj = a.mode != FIDM_STEP_UPDATE_ONLY;
+    const bool need_var = upd && a.var_type != FIDM_VAR_FIXED && (a.sampler == FIDM_SAMPLER_DDPM || a.logvar_out != nullptr);
+    const bool need_z = upd && (a.z != nullptr);
+    const int oc = (a.var_type == FIDM_VAR_FIXED) ? a.channels : 2 * a.channels;
+    const long long ooff = ((long long)b * oc + c) * a.hw + (long long)pv * VEC;
+    const int mc = (a.mask_channels == 1) ? 0 : c;
+    const long long moff = ((long long)b * a.mask_channels + mc) * a.hw + (long long)pv * VEC;
+    float xs[VEC], mo[VEC], vv[VEC], zz[VEC], g[VEC], n[VEC], m[VEC];
     load_vec<float, VEC>(a.x + off, xs);
+    if (upd) load_vec<float, VEC>(a.model_out + ooff, mo);
+    if (need_var) load_vec<float, VEC>(a.model_out + ooff + (long long)a.channels * a.hw, vv);
+    if (need_z) load_vec<float, VEC>(a.z + off, zz);
+    if (inj) {
+      load_vec<float, VEC>(a.gt + off, g);
+      load_vec<float, VEC>(a.inject_noise + off, n);
+      load_vec<float, VEC>(a.keep_mask + moff, m);
+    }
     float smp[VEC], x0v[VEC];
 
-    if (a.mode != FIDM_STEP_INJECT_ONLY) {
+    if (upd) {
       const float* cf = a.coef + (long long)t_upd * FIDM_COEF_COLS;
-      const int oc = (a.var_type == FIDM_VAR_FIXED) ? a.channels : 2 * a.channels;
-      const long long ooff = ((long long)b * oc + c) * a.hw + (long long)pv * VEC;
-      float mo[VEC], vv[VEC], zz[VEC], mv[VEC], lv[VEC];
-      load_vec<float, VEC>(a.model_out + ooff, mo);
-      if (a.var_type != FIDM_VAR_FIXED) load_vec<float, VEC>(a.model_out + ooff + (long long)a.channels * a.hw, vv);
-      const bool need_z = (a.z != nullptr);
-      if (need_z) load_vec<float, VEC>(a.z + off, zz);
+      float mv[VEC], lv[VEC];
       const float c1 = cf[FIDM_C_RECIP], c2 = cf[FIDM_C_RECIPM1];
       const float k1 = cf[FIDM_C_POST1], k2 = cf[FIDM_C_POST2];
       const float nz = cf[FIDM_C_NONZERO];
@@ -58,8 +70,10 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
       for (int i = 0; i < VEC; ++i) {
         const float x = xs[i];
         // ---- log-variance (gaussian_diffusion.py:241-265)
-        float logvar;
-        if (a.var_type == FIDM_VAR_LEARNED_RANGE) {
+        float logvar = 0.0f;
+        if (!need_var && a.var_type != FIDM_VAR_FIXED) {
+          // log-variance not needed (DDIM update, caller does not ask for it)
+        } else if (a.var_type == FIDM_VAR_LEARNED_RANGE) {
           const float frac = __fmul_rn(__fadd_rn(vv[i], 1.0f), 0.5f);                 // (v + 1) / 2
           logvar = __fadd_rn(__fmul_rn(frac, cf[FIDM_C_MAX_LOG]),
                              __fmul_rn(__fsub_rn(1.0f, frac), cf[FIDM_C_MIN_LOG]));
@@ -120,12 +134,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
       const float* cf = a.coef + (long long)t_inj * FIDM_COEF_COLS;
       const float ca = a.cumulative ? cf[FIDM_C_SQRT_AB] : cf[FIDM_C_SQRT_AB_F32];
       const float cs = a.cumulative ? cf[FIDM_C_SQRT_1MAB] : cf[FIDM_C_SQRT_1MAB_F32];
-      const int mc = (a.mask_channels == 1) ? 0 : c;
-      const long long moff = ((long long)b * a.mask_channels + mc) * a.hw + (long long)pv * VEC;
-      float g[VEC], n[VEC], m[VEC], xn[VEC];
-      load_vec<float, VEC>(a.gt + off, g);
-      load_vec<float, VEC>(a.inject_noise + off, n);
-      load_vec<float, VEC>(a.keep_mask + moff, m);
+      float xn[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float wg = __fadd_rn(__fmul_rn(ca, g[i]), __fmul_rn(cs, n[i]));
