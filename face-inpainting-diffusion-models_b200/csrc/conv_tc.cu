@@ -581,7 +581,9 @@ extern "C" int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width
   // worth it only when the CTA pairs of the machine are (nearly) all busy: 8 x 16 pixel boxes, two per pair
   const long long units = (long long)batch * (height / 16) * (width / 16) *
                           (cout == 16 ? 1 : cout / (cout % 256 == 0 ? 256 : 128));
-  return units * 4 >= (long long)(fidm::num_sms() / 2) * 3 ? 1 : 0;
+  // FIDM_HALO_MIN_FILL: percent of the CTA pairs that must have a unit (default 75)
+  static const int min_fill = getenv("FIDM_HALO_MIN_FILL") ? atoi(getenv("FIDM_HALO_MIN_FILL")) : 75;
+  return units * 100 >= (long long)(fidm::num_sms() / 2) * min_fill ? 1 : 0;
 }
 
 extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
