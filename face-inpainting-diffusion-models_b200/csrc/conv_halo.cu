@@ -10,7 +10,7 @@
 //
 //   * An M tile is an 8 x 16 box of output pixels of one image.  For every 64-channel slice ONE TMA box load
 //     fetches the 10 x 18 halo tile of the RAW bf16 stream (out-of-image pixels are zero-filled by the hardware).
-//   * Four transform warps read the halo tile once, apply h = x*A' + B' ; y = h + h*tanh(h)  (= silu(x*A + B) with
+//   * Five transform warps read the halo tile once, apply h = x*A' + B' ; y = h + h*tanh(h)  (= silu(x*A + B) with
 //     A' = A/2, B' = B/2: one MUFU op), force the conv's zero padding (out-of-image pixels are 0 AFTER the
 //     activation), and write three column-shifted copies (s = 0,1,2) of [18 rows][8 pixels][64 ch] 16-bit in the
 //     canonical K-major 128-byte-swizzled UMMA layout.  A row of a copy is exactly one 1024-byte swizzle atom, so
@@ -20,6 +20,11 @@
 //   * CTA pair (cta_group::2): each CTA transforms its own 128 pixel rows and stages half of the weight tile.
 //   * Epilogue = K1's (bias, timestep row, residual, bf16 TMA store into concat slices, fused GroupNorm statistics
 //     of the output).
+//   * UP: `up` ResBlocks (nn.py:190-195) -- the halo tile is the 6 x 10 box of the HALF-resolution stream it covers
+//     after a nearest 2x upsample; every source pixel is activated once and stored to its 2 x 2 halo positions.  The
+//     second conv of the block reads its identity skip at (h/2, w/2) (res_half).  BLOCK_N = 16: the 6-channel head
+//     (unet.py:148-152) with fp32 NCHW stores.  BLOCK_N = 128: Cout % 256 != 0 (runs at half the tensor rate: a
+//     tcgen05.mma with the A operand in shared memory takes as long for N = 128 as for N = 256).
 //
 // Warp roles (512 threads): warps 0-7 epilogue (two warpgroups), 8-12 transform, 13 weight-ring TMA producer,
 // 14 MMA issuer (+ TMEM owner), 15 halo TMA producer.  128 registers per thread suit every role.
