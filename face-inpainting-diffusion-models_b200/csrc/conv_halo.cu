@@ -48,6 +48,7 @@ struct ConvHaloParams {
   const float* bias;
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
+  int res_tma;              // residual tile fetched by TMA into the staging buffer (full-resolution residual)
   int res_half;             // residual is stored at HALF resolution (x_upd of an up ResBlock, nn.py:194): read (h/2, w/2)
   float* colsum; int colsum_slots; int cout;
   float* y_nchw; int cout_valid;     // BLOCK_N == 16 (the 6-channel head, unet.py:151): fp32 NCHW output of cout_valid channels
@@ -109,7 +110,8 @@ template <int BLOCK_N, bool OUT_F16, bool UP>
 __global__ void __launch_bounds__(halo::kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                 const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
+                 const ConvHaloParams p) {
   using namespace halo;
   constexpr int kBBytes = (BLOCK_N / 2) * 128;           // this CTA's half of one weight tile
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -131,7 +133,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   uint64_t* const ring_empty = bars + 10 + kRingStages;
   uint64_t* const tmem_full = bars + 10 + 2 * kRingStages;    // [2]
   uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* const res_bar = tmem_empty + 2;                   // [2]  residual tile landed in a warpgroup's staging buffer
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();          // rank 0 = leader (issues the MMAs)
@@ -146,6 +149,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
     tma_prefetch_desc(&tmB);
     if (p.kc2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     if (BLOCK_N >= 64) tma_prefetch_desc(&tmY);
+    if (BLOCK_N >= 64 && p.res_tma) tma_prefetch_desc(&tmRes);
   }
   if (warp == 14) {
     if (lane == 0) {
@@ -153,6 +157,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
       for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 2); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+      for (int i = 0; i < 2; ++i) mbar_init(&res_bar[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -461,6 +466,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
     const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
     uint8_t* const stage_out = staging + wg * kStagingBytes;
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
     long long pf_full = 0, pf_t;
     const long long pf_start = clock64();
     for (int wu = unit; wu < total_units; wu += n_units) {
@@ -502,6 +508,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
 #pragma unroll 1
       for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
         const int cbase = co0 + ch * 64;
+        if (p.res_tma) {
+          // The residual tile of this chunk travels by TMA into the (idle) staging buffer while the accumulator is
+          // drained: 268 MB exactly once through the L2 -> SM path, instead of per-thread 16-byte loads through an L1
+          // that the 218 KB shared-memory carve-out leaves too small to keep a 128-byte row alive between them.
+          named_bar_sync(bar_a, 128);                        // nobody still reads the buffer (statistics of the last chunk)
+          if (issuer) {
+            bulk_wait_group_read<0>();                       // the previous TMA store has finished reading it too
+            mbar_expect_tx(&res_bar[wg], kStagingBytes);
+            tma_load_4d(&tmRes, &res_bar[wg], stage_out, cbase, w0, h0, n);
+          }
+        }
         float f[64];
         {
           uint32_t v0[32], v1[32];
@@ -532,7 +549,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
             f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
           }
         }
-        if (p.residual) {
+        if (p.res_tma) {
+          mbar_wait(&res_bar[wg], res_phase);
+          res_phase ^= 1u;
+          const uint32_t rrow = smem_u32(stage_out) + row * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t u1, u2, u3;
+            const uint32_t u0 = ld_shared_u32x4(rrow + ((q ^ (row & 7)) << 4), u1, u2, u3);
+            const uint32_t u[4] = {u0, u1, u2, u3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[8 * q + 2 * e] += __uint_as_float(u[e] << 16);
+              f[8 * q + 2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u);
+            }
+          }
+        } else if (p.residual) {
           const uint4* rs = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + cbase);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -629,12 +661,14 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.res_half = a.residual_half_res;
+  static const bool res_tma_ok = getenv("FIDM_HALO_RES_TMA") == nullptr || atoi(getenv("FIDM_HALO_RES_TMA")) != 0;
+  p.res_tma = (BLOCK_N >= 64 && a.residual && !a.residual_half_res && res_tma_ok) ? 1 : 0;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 2;
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
   p.prof = g_prof;
 
-  CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY;
+  CUtensorMap tmRaw, tmB, tmA2, tmB2, tmY, tmRes;
   int rc;
   // the raw stream is bf16; only the element SIZE matters to the copy engine
   if (UP) {
@@ -654,6 +688,10 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   } else {
     tmY = tmB;
   }
+  tmRes = tmB;
+  if (p.res_tma) {
+    if ((rc = make_nhwc_map(&tmRes, a.residual, a.cout, a.width, a.height, a.batch, a.ld_res, kTW, kTH, 1, 0))) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     FIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, OUT_F16, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -672,7 +710,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16, UP>, tmRaw, tmB, tmA2, tmB2, tmY, p));
+  FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, OUT_F16, UP>, tmRaw, tmB, tmA2, tmB2, tmY, tmRes, p));
   FIDM_CHECK_LAUNCH("conv_halo");
   return 0;
 }
