@@ -378,10 +378,10 @@ def dominant_kernel_roofline(ops, dev, pk, B):
             "peak_src": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": ms,
             "flops_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at batch 8 from the committed
-            # `ncu --set full` capture (profiles/r1_ncu_full_conv_halo.txt): 271.2 MB + 239.4 MB; the algorithmic
+            # `ncu --set full` capture (profiles/r1d_ncu_full_conv_halo.txt): 269.7 MB + 238.7 MB; the algorithmic
             # minimum is 268.4 MB in + 268.4 MB out + 1.2 MB of weights
-            "traffic": 510.6e6 * B / 8, "traffic_src": "profiles/r1_ncu_full_conv_halo.txt",
-            "tensor_pipe_active_pct_ncu": 83.7,
+            "traffic": 508.4e6 * B / 8, "traffic_src": "profiles/r1d_ncu_full_conv_halo.txt",
+            "tensor_pipe_active_pct_ncu": 84.6,
             "k1_same_layer_prenormalized_operand": {"ms_per_launch": ms_k1, "achieved": flops / (ms_k1 * 1e-3) / 1e12}}
 
 
