@@ -83,6 +83,7 @@ SYMBOLS = {
     "fidm_groupnorm_workspace_bytes": (C.c_int64, [i32, i32]),
     "fidm_groupnorm_reduce_colsum": (C.c_int, [fp, i32, i32, i32, fp, i32, i32, vp]),
     "fidm_groupnorm_silu_coeff": (C.c_int, [_P(GnArgs), fp, i32, vp]),
+    "fidm_groupnorm_reduce_colsum_coeff": (C.c_int, [fp, i32, fp, i32, i32, _P(GnArgs), fp, i32, vp]),
     "fidm_conv_colsum_slots": (C.c_int, [i32, i32]),
     "fidm_conv_gn_fusable": (C.c_int, [i32, i32, i32, i32, i32, i32, i32]),
     "fidm_conv2d_nhwc_bf16": (C.c_int, [_P(ConvArgs), vp]),

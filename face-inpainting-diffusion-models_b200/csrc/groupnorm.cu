@@ -23,10 +23,27 @@ struct GnParams {
   int pix_per_blk; // pixels (of the iteration space) per block
 };
 
+// Halved affine coefficients of GroupNorm [* (1+scale) + shift] followed by SiLU for channel c of image n
+// (silu(x*A + B) = h + h*tanh(h), h = x*A/2 + B/2): what the K1h conv applies in its operand path.
+__device__ __forceinline__ float2 gn_half_coeff(const fidm_gn_args& a, int n, int c, float meanf, float rstd) {
+  const float ga = a.gamma ? a.gamma[c] : 1.0f;
+  const float be = a.beta ? a.beta[c] : 0.0f;
+  float Ai = rstd * ga;
+  float Bi = be - meanf * Ai;
+  if (a.scale_shift) {
+    const float sc = 1.0f + a.scale_shift[(long long)n * a.ld_ss + c];
+    const float sh = a.scale_shift[(long long)n * a.ld_ss + a.channels + c];
+    Ai *= sc;
+    Bi = Bi * sc + sh;
+  }
+  return make_float2(0.5f * Ai, 0.5f * Bi);
+}
+
 // Pass 1: per-block partial (sum, sum of squares) of every group, reduced in a FIXED order (no
 // atomics) so that results are bit-reproducible run to run.  partials: [batch][chunks][groups][2].
 template <typename T, int VEC>
-__global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials, int* __restrict__ counters) {
+__global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials, int* __restrict__ counters,
+                                float2* __restrict__ coef, int ld_coef) {
   const fidm_gn_args& a = p.a;
   extern __shared__ float red[];           // [blockDim][2]
   const int n = blockIdx.y;
@@ -118,14 +135,22 @@ __global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials,
     mr[0] = (float)mean;
     mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
+  if (coef) {      // statistics-only call: the last block also writes the per-channel coefficients (no extra launch)
+    __threadfence_block();
+    __syncthreads();
+    const float* mr = reinterpret_cast<const float*>(a.stats) + (long long)n * G * 2;
+    for (int c = threadIdx.x; c < a.channels; c += blockDim.x)
+      coef[(long long)n * ld_coef + c] = gn_half_coeff(a, n, c, mr[2 * (c / cpg)], mr[2 * (c / cpg) + 1]);
+  }
 }
 
 // Small tensors (L2-resident): one block per (image, group) reads that group's channel slice of every pixel
 // and reduces it in a fixed tree -- no workspace, no cross-block step, one short launch.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) gn_stats_direct_kernel(const GnParams p) {
+__global__ void __launch_bounds__(256) gn_stats_direct_kernel(const GnParams p, float2* __restrict__ coef, int ld_coef) {
   const fidm_gn_args& a = p.a;
   __shared__ double red[8][2];
+  __shared__ float mr_s[2];
   const int g = blockIdx.x, n = blockIdx.y;
   const int hw = a.height * a.width;
   const int cpg = a.channels / a.groups;
@@ -160,8 +185,13 @@ __global__ void __launch_bounds__(256) gn_stats_direct_kernel(const GnParams p) 
     double var = a1 / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     float* mr = reinterpret_cast<float*>(a.stats) + ((long long)n * a.groups + g) * 2;
-    mr[0] = (float)mean;
-    mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+    mr[0] = mr_s[0] = (float)mean;
+    mr[1] = mr_s[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  if (coef) {      // statistics-only call: this block writes the coefficients of its group's channels (no extra launch)
+    __syncthreads();
+    for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 256)
+      coef[(long long)n * ld_coef + c] = gn_half_coeff(a, n, c, mr_s[0], mr_s[1]);
   }
 }
 
@@ -475,17 +505,7 @@ __global__ void __launch_bounds__(256) gn_coeff_kernel(const fidm_gn_args a, flo
   __syncthreads();
   for (int c = threadIdx.x; c < a.channels; c += blockDim.x) {
     const float2 mr = mr_s[c / cpg];
-    const float ga = a.gamma ? a.gamma[c] : 1.0f;
-    const float be = a.beta ? a.beta[c] : 0.0f;
-    float Ai = mr.y * ga;
-    float Bi = be - mr.x * Ai;
-    if (a.scale_shift) {
-      const float sc = 1.0f + a.scale_shift[(long long)n * a.ld_ss + c];
-      const float sh = a.scale_shift[(long long)n * a.ld_ss + a.channels + c];
-      Ai *= sc;
-      Bi = Bi * sc + sh;
-    }
-    coef[(long long)n * ld_coef + c] = make_float2(0.5f * Ai, 0.5f * Bi);
+    coef[(long long)n * ld_coef + c] = gn_half_coeff(a, n, c, mr.x, mr.y);
   }
 }
 
@@ -510,7 +530,7 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
   };
   int chunks;
   if (!a.skip_norm && !a.chansum && (long long)hw * (a.channels / a.groups) <= 32768) {    // <= 64 KB per (image, group) block
-    gn_stats_direct_kernel<T, VEC><<<dim3(a.groups, a.batch), 256, 0, st>>>(p);
+    gn_stats_direct_kernel<T, VEC><<<dim3(a.groups, a.batch), 256, 0, st>>>(p, coef, ld_coef);
     FIDM_CHECK_LAUNCH("groupnorm stats (direct)");
   } else if (!a.skip_norm && !a.chansum) {
     // workspace: [batch*groups*2] floats (mean, rstd) padded to doubles, then the per-block partials
@@ -524,12 +544,14 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
     const long long blocks_cap = (FIDM_GN_MAX_BLOCKS > a.batch ? FIDM_GN_MAX_BLOCKS : a.batch) + a.batch;
     int* counters = reinterpret_cast<int*>(partials + blocks_cap * a.groups * 2);
     gn_stats_kernel<T, VEC><<<dim3(chunks, a.batch), threads, sizeof(float) * 2 * threads + 8 * 64 * 2 * sizeof(double), st>>>(
-        p, partials, counters);
+        p, partials, counters, coef, ld_coef);
     FIDM_CHECK_LAUNCH("groupnorm stats");
   }
   if (coef) {      // statistics only: the consumer conv applies the activation in its operand path
-    gn_coeff_kernel<<<a.batch, 256, 0, st>>>(a, coef, ld_coef);
-    FIDM_CHECK_LAUNCH("groupnorm coeff");
+    if (a.chansum) {         // (the statistics kernels above wrote the coefficients themselves)
+      gn_coeff_kernel<<<a.batch, 256, 0, st>>>(a, coef, ld_coef);
+      FIDM_CHECK_LAUNCH("groupnorm coeff");
+    }
     return 0;
   }
   chunks = plan(it_hw);
@@ -608,8 +630,11 @@ namespace fidm {
 // chansum[n][c0+c] = sum_{slot} colsum[n][slot][c]   (double accumulation, fixed order)
 constexpr int RS = 32;   // slices of the slot range per block (fixed summation tree: slice, then slices in order)
 __global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2* __restrict__ colsum, int slots, int C,
-                                                                   float2* __restrict__ chansum, int ld, int c0) {
+                                                                   float2* __restrict__ chansum, int ld, int c0,
+                                                                   const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
   __shared__ double red[RS][32][2];
+  __shared__ double csum[32][2];
+  __shared__ float2 mr_s[32];
   const int n = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int j = threadIdx.x >> 5;
@@ -631,11 +656,34 @@ __global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2*
   red[j][threadIdx.x & 31][0] = ds;
   red[j][threadIdx.x & 31][1] = dss;
   __syncthreads();
-  if (j == 0 && c < C) {
-    double a = 0.0, b = 0.0;
+  if (j == 0) {
+    double sa = 0.0, sb = 0.0;
 #pragma unroll
-    for (int k = 0; k < RS; ++k) { a += red[k][threadIdx.x][0]; b += red[k][threadIdx.x][1]; }
-    chansum[(long long)n * ld + c0 + c] = make_float2((float)a, (float)b);
+    for (int k = 0; k < RS; ++k) { sa += red[k][threadIdx.x][0]; sb += red[k][threadIdx.x][1]; }
+    // the consumer sees the sums rounded to fp32 (chansum): fold exactly those, as gn_coeff_kernel would
+    csum[threadIdx.x][0] = (double)(float)sa;
+    csum[threadIdx.x][1] = (double)(float)sb;
+    if (c < C) chansum[(long long)n * ld + c0 + c] = make_float2((float)sa, (float)sb);
+  }
+  if (!coef) return;
+  // Single-producer case: this tensor IS the GroupNorm input of the next conv (K1h), and every group lies inside one
+  // block's 32 channels: fold the groups here and write the coefficients -- no separate coefficient launch.
+  __syncthreads();
+  const int cpg = a.channels / a.groups;
+  const int gpb = 32 / cpg;                               // groups per block
+  if (threadIdx.x < gpb) {
+    double gs = 0.0, gss = 0.0;
+    for (int k = 0; k < cpg; ++k) { gs += csum[threadIdx.x * cpg + k][0]; gss += csum[threadIdx.x * cpg + k][1]; }
+    const double cnt = (double)cpg * a.height * a.width;
+    const double mean = gs / cnt;
+    double var = gss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mr_s[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+  }
+  __syncthreads();
+  if (j == 0 && c < C) {
+    const float2 mr = mr_s[threadIdx.x / cpg];
+    coef[(long long)n * ld_coef + c] = gn_half_coeff(a, n, c, mr.x, mr.y);
   }
 }
 }  // namespace fidm
@@ -646,9 +694,31 @@ extern "C" int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, 
   FIDM_REQUIRE(colsum && chansum && batch > 0 && slots > 0 && channels > 0 && c0 >= 0 && c0 + channels <= ld_chansum,
                FIDM_E_BADARG, "reduce_colsum: bad args");
   dim3 grid((channels + 31) / 32, batch);
+  fidm_gn_args none = {};
   gn_reduce_colsum_kernel<<<grid, 32 * RS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(colsum), slots, channels,
-                                                                 reinterpret_cast<float2*>(chansum), ld_chansum, c0);
+                                                                 reinterpret_cast<float2*>(chansum), ld_chansum, c0, none,
+                                                                 nullptr, 0);
   FIDM_CHECK_LAUNCH("reduce_colsum");
+  return 0;
+}
+
+extern "C" int fidm_groupnorm_reduce_colsum_coeff(const float* colsum, int32_t slots, float* chansum, int32_t ld_chansum,
+                                                  int32_t c0, const fidm_gn_args* a, float* coef, int32_t ld_coef,
+                                                  fidm_stream_t stream) {
+  using namespace fidm;
+  FIDM_REQUIRE(colsum && chansum && a && coef && slots > 0 && c0 >= 0 && c0 + a->channels <= ld_chansum, FIDM_E_BADARG,
+               "reduce_colsum_coeff: bad args");
+  FIDM_REQUIRE(a->groups > 0 && a->channels % a->groups == 0 && a->channels % 32 == 0, FIDM_E_SHAPE,
+               "reduce_colsum_coeff: channels %d / groups %d", a->channels, a->groups);
+  const int cpg = a->channels / a->groups;
+  FIDM_REQUIRE(cpg <= 32 && 32 % cpg == 0, FIDM_E_SHAPE, "reduce_colsum_coeff: %d channels per group do not tile 32", cpg);
+  FIDM_REQUIRE(ld_coef >= a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_coef");
+  if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_ss < 2*channels");
+  dim3 grid(a->channels / 32, a->batch);
+  gn_reduce_colsum_kernel<<<grid, 32 * RS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(colsum), slots,
+                                                                 a->channels, reinterpret_cast<float2*>(chansum), ld_chansum,
+                                                                 c0, *a, reinterpret_cast<float2*>(coef), ld_coef);
+  FIDM_CHECK_LAUNCH("reduce_colsum_coeff");
   return 0;
 }
 

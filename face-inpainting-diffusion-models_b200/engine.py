@@ -181,6 +181,7 @@ class Plan:
         # GroupNorm + SiLU applied in the consumer conv's operand path (K1h) where fidm_conv_gn_fusable() says so
         self.fuse_gn = os.environ.get("FIDM_FUSE_GN_APPLY", "1") != "0"
         self.fuse_up = os.environ.get("FIDM_FUSE_UPSAMPLE", "1") != "0"
+        self.fuse_reduce_coeff = os.environ.get("FIDM_FUSE_REDUCE_COEFF", "1") != "0"
         self.chansum = {}        # id(storage) -> fp32 [B, ld, 2]
         self.coverage = {}       # id(storage) -> [(c0, channels)]
         self.colsum_scratch = {}  # numel -> fp32 scratch for the per-tile partial rows
@@ -212,6 +213,7 @@ class Plan:
                  B, ted, ted, 1)
         self._op(lib.fidm_linear_small, L.ptr(self.emb), L.ptr(w.emb_w), L.F32, L.ptr(w.emb_b), L.ptr(self.emb_all),
                  B, ted, w.emb_total, 1)
+        self._last_reduce = None             # (op index, storage id, c0, channels, colsum ptr, slots, chansum) of the last fold
         self.n_time_ops = len(self.ops)      # K5 depends only on t: a parallel branch of the graph (see launch_all)
         self.first_emb_use = None            # index of the first op that reads emb_all
 
@@ -343,7 +345,19 @@ class Plan:
             cs = self.chansum[id(x.storage)]
             a.chansum, a.ld_chansum = L.ptr(cs, x.c0 * 8), cs.shape[1]
         self.keep.append((a, coef))
-        self._op(self.lib.fidm_groupnorm_silu_coeff, C.byref(a), L.ptr(coef), x.channels)
+        lr = self._last_reduce
+        cpg = x.channels // 32
+        if (lr is not None and lr[0] == len(self.ops) - 1 and lr[1:4] == (id(x.storage), x.c0, x.channels) and
+                x.channels % 32 == 0 and cpg <= 32 and 32 % cpg == 0 and self.fuse_reduce_coeff):
+            # x was produced by the conv just before and its statistics were folded by the previous op: redo that
+            # fold together with the coefficients (one launch instead of two, identical results)
+            self.ops.pop()
+            _, _, c0, ch, colsum, slots, cs = lr
+            self._op(self.lib.fidm_groupnorm_reduce_colsum_coeff, colsum, slots, L.ptr(cs), cs.shape[1], c0, C.byref(a),
+                     L.ptr(coef), x.channels)
+            self._last_reduce = None
+        else:
+            self._op(self.lib.fidm_groupnorm_silu_coeff, C.byref(a), L.ptr(coef), x.channels)
         return coef
 
     def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
@@ -406,6 +420,7 @@ class Plan:
                 self.chansum[sid] = torch.zeros(self.B, y.ld, 2, device=w.device, dtype=torch.float32)
             cs = self.chansum[sid]
             self._op(self.lib.fidm_groupnorm_reduce_colsum, a.colsum, self.B, slots, cout_pad, L.ptr(cs), y.ld, y.c0)
+            self._last_reduce = (len(self.ops) - 1, sid, y.c0, cout_pad, a.colsum, slots, cs)
             self.coverage.setdefault(sid, []).append((y.c0, cout_pad))
         elif y is not None:
             # a producer without fused statistics invalidates whatever was recorded for these channels
@@ -424,7 +439,7 @@ class Plan:
         self._op(fn, C.byref(a))
 
     TC_ATTENTION = True
-    FUSE_MIN_PIXELS = 128 * 128
+    FUSE_MIN_PIXELS = int(os.environ.get("FIDM_FUSE_MIN_PIXELS", 128 * 128))
 
     # ------------------------------------------------------------------ layers
     def _block(self, blk, x, dst):
@@ -609,7 +624,7 @@ class Plan:
             if fn is self.lib.fidm_groupnorm_silu_nhwc:
                 n += self.lib.fidm_groupnorm_num_launches(args[0])
             elif fn is self.lib.fidm_groupnorm_silu_coeff:
-                n += 1 if args[0]._obj.chansum else 2
+                n += 1
             else:
                 n += 1
         return n

@@ -190,6 +190,11 @@ int fidm_groupnorm_silu_coeff(const fidm_gn_args* a, float* coef, int32_t ld_coe
 /* chansum[n][c0 + c] = sum over the `slots` partial rows of image n of colsum[n][slot][c]  (fixed order) */
 int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, int32_t slots, int32_t channels,
                                  float* chansum, int32_t ld_chansum, int32_t c0, fidm_stream_t stream);
+/* The same fold, and -- when the reduced tensor IS the input of the next GroupNorm (`a`: batch/height/width/channels/
+ * groups/eps/gamma/beta/scale_shift of that norm; channels % 32 == 0, channels/groups divides 32) -- the coefficients
+ * fidm_groupnorm_silu_coeff would compute from chansum, bit-identical, in the same launch. */
+int fidm_groupnorm_reduce_colsum_coeff(const float* colsum, int32_t slots, float* chansum, int32_t ld_chansum, int32_t c0,
+                                       const fidm_gn_args* a, float* coef, int32_t ld_coef, fidm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  convolution as implicit GEMM, NHWC activations, KRSC weights ([Cout][kh][kw][Cin]).

@@ -289,3 +289,26 @@ def test_fused_groupnorm_plan_equals_unfused_plan(cuda_lib, name, B, monkeypatch
     # two bf16 evaluations with different (equivalent) rounding points differ from each other by about sqrt(2) x
     # their distance to the fp32 oracle (5-7e-3): 1 ulp flips of stored bf16 values propagate through ~40 layers
     assert rel_l2(outs["1"], outs["0"]) < 1e-2
+
+
+def test_fused_reduce_coeff_is_bit_identical(cuda_lib, monkeypatch):
+    """Folding the producer's partial channel sums and computing the consumer's GroupNorm coefficients in ONE launch
+    (fidm_groupnorm_reduce_colsum_coeff) must give exactly the bits of the two-launch path."""
+    import fidm_b200 as F
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    cfg = F.CONFIGS["REF_FFHQ256"]
+    sd = synth_state_dict(cfg, seed=3)
+    B = 2
+    data = synth_batch(B, 256, seed=6, device=DEV)
+    x = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(8)).to(DEV)
+    t = torch.tensor([12] * B, device=DEV)
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("FIDM_FUSE_REDUCE_COEFF", fused)
+        m = _model(cfg, sd, "bf16")
+        outs[fused] = m(x, t, masked_image=data["masked_image"], mask=data["mask"]).clone()
+        plan = m.base_model.plan_for(B, 256, 256)
+        n_fused = sum(1 for fn, _ in plan.ops if fn is plan.lib.fidm_groupnorm_reduce_colsum_coeff)
+        assert (n_fused > 0) == (fused == "1")
+        del m
+    assert torch.equal(outs["1"], outs["0"])
