@@ -79,6 +79,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // nothing below may touch global memory before that kernel has completed.
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
   if (warp == 4) {
@@ -268,7 +272,7 @@ extern "C" int fidm_attention_qkv_nhwc_bf16(const fidm_attn_args* a, fidm_stream
     attr_set = true;
   }
   dim3 grid((a->tokens + BQ - 1) / BQ, a->heads, a->batch);
-  attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(tmQKV, tmO, p);
+  FIDM_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, tmQKV, tmO, p));
   FIDM_CHECK_LAUNCH("attention_tc");
   return 0;
 }

@@ -77,6 +77,44 @@ __device__ __forceinline__ void store_vec(T* p, const float (&in)[V]) {
   *reinterpret_cast<Vec<T, V>*>(p) = t;
 }
 
+// ---- programmatic dependent launch (PDL), opt-in with FIDM_PDL=1.  The kernels of the UNet call pdl_wait() before their
+// first access to global memory that an earlier kernel may have written (or may still read), so they MAY be launched
+// with the programmatic-stream-serialization attribute: the launch, the block scheduling and the prologue (barrier
+// init, TMEM allocation, descriptor prefetch) then overlap the tail of the predecessor.  Measured inside the CUDA graph
+// of one evaluation it bought nothing (the graph's launch gaps are already ~1 us), so the attribute is off by default
+// and pdl_wait() is a no-op; pdl_trigger() (FIDM_PDL_TRIGGER) made things slower and compiles to nothing.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef FIDM_PDL_TRIGGER
+#define FIDM_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if FIDM_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+bool pdl_enabled();          // FIDM_PDL=0 switches the attribute off (the device-side calls are then no-ops)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

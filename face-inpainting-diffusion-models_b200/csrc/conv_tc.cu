@@ -116,6 +116,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // nothing below may touch global memory before that kernel has completed.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 8) {
     // ===================================================================== TMA producer
@@ -542,21 +546,8 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   const int units = ((m_tiles + CG - 1) / CG) * p.n_blocks * split_k;  // (tile | tile pair) x K split
   const int slots = num_sms() / CG;
   const int grid = (units < slots ? units : slots) * CG;
-  if (CG == 1) {
-    conv_tc_kernel<BLOCK_N, CG><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmA2, tmB2, tmY, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    FIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG>, tmA, tmB, tmA2, tmB2, tmY, p));
-  }
+  FIDM_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, CG, tmA, tmB, tmA2, tmB2,
+                       tmY, p));
   FIDM_CHECK_LAUNCH("conv_tc");
   return 0;
 }

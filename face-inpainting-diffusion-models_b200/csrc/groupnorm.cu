@@ -44,6 +44,8 @@ __device__ __forceinline__ float2 gn_half_coeff(const fidm_gn_args& a, int n, in
 template <typename T, int VEC>
 __global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials, int* __restrict__ counters,
                                 float2* __restrict__ coef, int ld_coef) {
+  pdl_wait();
+  pdl_trigger();
   const fidm_gn_args& a = p.a;
   extern __shared__ float red[];           // [blockDim][2]
   const int n = blockIdx.y;
@@ -148,6 +150,8 @@ __global__ void gn_stats_kernel(const GnParams p, double* __restrict__ partials,
 // and reduces it in a fixed tree -- no workspace, no cross-block step, one short launch.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) gn_stats_direct_kernel(const GnParams p, float2* __restrict__ coef, int ld_coef) {
+  pdl_wait();
+  pdl_trigger();
   const fidm_gn_args& a = p.a;
   __shared__ double red[8][2];
   __shared__ float mr_s[2];
@@ -212,6 +216,8 @@ __device__ __forceinline__ float silu_f(float v) {
 // per thread (NV * blockDim vectors per (image, group)).
 template <typename TY, int NV>
 __global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double red[16][2];
   __shared__ float mr[2];
   constexpr bool FAST = true;
@@ -323,15 +329,17 @@ static int try_gn_fused_small(const fidm_gn_args& a, cudaStream_t st) {
   int vpp, threads, stride, per_thread;
   if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread)) return -1;
   dim3 grid(a.groups, a.batch);
-  if (per_thread <= 2) gn_fused_small_kernel<TY, 2><<<grid, threads, 0, st>>>(a, vpp, stride);
-  else if (per_thread <= 4) gn_fused_small_kernel<TY, 4><<<grid, threads, 0, st>>>(a, vpp, stride);
-  else gn_fused_small_kernel<TY, 8><<<grid, threads, 0, st>>>(a, vpp, stride);
+  if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
+  else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
+  else launch_pdl(gn_fused_small_kernel<TY, 8>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   FIDM_CHECK_LAUNCH("groupnorm (fused small)");
   return 0;
 }
 
 template <typename T, typename TY, int VEC, int RESAMPLE>
 __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnParams p) {
+  pdl_wait();
+  pdl_trigger();
   const fidm_gn_args& a = p.a;
   constexpr bool FAST = (sizeof(T) == 2);
   const int n = blockIdx.y;
@@ -479,6 +487,8 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnParams p) {
 // (silu(x*A + B) = h + h*tanh(h), h = x*A/2 + B/2).  Same arithmetic as the head of gn_apply_kernel, so a conv that
 // applies the activation in its operand path sees exactly the coefficients the apply pass would have used.
 __global__ void __launch_bounds__(256) gn_coeff_kernel(const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float2 mr_s[64];
   const int n = blockIdx.x;
   const int hw = a.height * a.width;
@@ -530,7 +540,7 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
   };
   int chunks;
   if (!a.skip_norm && !a.chansum && (long long)hw * (a.channels / a.groups) <= 32768) {    // <= 64 KB per (image, group) block
-    gn_stats_direct_kernel<T, VEC><<<dim3(a.groups, a.batch), 256, 0, st>>>(p, coef, ld_coef);
+    launch_pdl(gn_stats_direct_kernel<T, VEC>, dim3(a.groups, a.batch), dim3(256), 0, st, 1, p, coef, ld_coef);
     FIDM_CHECK_LAUNCH("groupnorm stats (direct)");
   } else if (!a.skip_norm && !a.chansum) {
     // workspace: [batch*groups*2] floats (mean, rstd) padded to doubles, then the per-block partials
@@ -543,13 +553,13 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
     }
     const long long blocks_cap = (FIDM_GN_MAX_BLOCKS > a.batch ? FIDM_GN_MAX_BLOCKS : a.batch) + a.batch;
     int* counters = reinterpret_cast<int*>(partials + blocks_cap * a.groups * 2);
-    gn_stats_kernel<T, VEC><<<dim3(chunks, a.batch), threads, sizeof(float) * 2 * threads + 8 * 64 * 2 * sizeof(double), st>>>(
-        p, partials, counters, coef, ld_coef);
+    launch_pdl(gn_stats_kernel<T, VEC>, dim3(chunks, a.batch), dim3(threads),
+               sizeof(float) * 2 * threads + 8 * 64 * 2 * sizeof(double), st, 1, p, partials, counters, coef, ld_coef);
     FIDM_CHECK_LAUNCH("groupnorm stats");
   }
   if (coef) {      // statistics only: the consumer conv applies the activation in its operand path
     if (a.chansum) {         // (the statistics kernels above wrote the coefficients themselves)
-      gn_coeff_kernel<<<a.batch, 256, 0, st>>>(a, coef, ld_coef);
+      launch_pdl(gn_coeff_kernel, dim3(a.batch), dim3(256), 0, st, 1, a, coef, ld_coef);
       FIDM_CHECK_LAUNCH("groupnorm coeff");
     }
     return 0;
@@ -558,11 +568,11 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
   dim3 grid(chunks, a.batch);
   const size_t sm = a.chansum ? sizeof(float2) * (a.channels + a.groups) : 0;
   if (a.resample == FIDM_RESAMPLE_NONE)
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_NONE><<<grid, threads, sm, st>>>(p);
+    launch_pdl(gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_NONE>, grid, dim3(threads), sm, st, 1, p);
   else if (a.resample == FIDM_RESAMPLE_DOWN)
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_DOWN><<<grid, threads, sm, st>>>(p);
+    launch_pdl(gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_DOWN>, grid, dim3(threads), sm, st, 1, p);
   else
-    gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_UP><<<grid, threads, sm, st>>>(p);
+    launch_pdl(gn_apply_kernel<T, TY, VEC, FIDM_RESAMPLE_UP>, grid, dim3(threads), sm, st, 1, p);
   FIDM_CHECK_LAUNCH("groupnorm apply");
   return 0;
 }
@@ -632,6 +642,8 @@ constexpr int RS = 32;   // slices of the slot range per block (fixed summation 
 __global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2* __restrict__ colsum, int slots, int C,
                                                                    float2* __restrict__ chansum, int ld, int c0,
                                                                    const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double red[RS][32][2];
   __shared__ double csum[32][2];
   __shared__ float2 mr_s[32];
@@ -695,9 +707,8 @@ extern "C" int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, 
                FIDM_E_BADARG, "reduce_colsum: bad args");
   dim3 grid((channels + 31) / 32, batch);
   fidm_gn_args none = {};
-  gn_reduce_colsum_kernel<<<grid, 32 * RS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(colsum), slots, channels,
-                                                                 reinterpret_cast<float2*>(chansum), ld_chansum, c0, none,
-                                                                 nullptr, 0);
+  launch_pdl(gn_reduce_colsum_kernel, grid, dim3(32 * RS), 0, (cudaStream_t)stream, 1, reinterpret_cast<const float2*>(colsum),
+             slots, channels, reinterpret_cast<float2*>(chansum), ld_chansum, c0, none, (float2*)nullptr, 0);
   FIDM_CHECK_LAUNCH("reduce_colsum");
   return 0;
 }
@@ -715,9 +726,8 @@ extern "C" int fidm_groupnorm_reduce_colsum_coeff(const float* colsum, int32_t s
   FIDM_REQUIRE(ld_coef >= a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_coef");
   if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_ss < 2*channels");
   dim3 grid(a->channels / 32, a->batch);
-  gn_reduce_colsum_kernel<<<grid, 32 * RS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(colsum), slots,
-                                                                 a->channels, reinterpret_cast<float2*>(chansum), ld_chansum,
-                                                                 c0, *a, reinterpret_cast<float2*>(coef), ld_coef);
+  launch_pdl(gn_reduce_colsum_kernel, grid, dim3(32 * RS), 0, (cudaStream_t)stream, 1, reinterpret_cast<const float2*>(colsum),
+             slots, a->channels, reinterpret_cast<float2*>(chansum), ld_chansum, c0, *a, reinterpret_cast<float2*>(coef), ld_coef);
   FIDM_CHECK_LAUNCH("reduce_colsum_coeff");
   return 0;
 }
