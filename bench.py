@@ -158,6 +158,10 @@ def main():
     ap.add_argument("--workload", default="adm256", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="images per GPU")
     ap.add_argument("--ddim-steps", type=int, default=None)
+    ap.add_argument("--schedule", default=None, choices=["cosine", "linear", "quadratic"],
+                    help="noise schedule (BASELINE configs[2]: linear, configs[4]: quadratic); default: the workload's")
+    ap.add_argument("--sampler", default="ddim", choices=["ddim", "ddpm"],
+                    help="ddpm: p_sample_loop over all --ddim-steps timesteps (BASELINE configs[2]: DDPM-1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-only", action="store_true", help="only time UNet evaluations (ms per eval)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -165,6 +169,10 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.ddim_steps:
         wl["ddim_steps"] = args.ddim_steps
+    if args.schedule:
+        wl["schedule"] = args.schedule
+    if args.schedule or args.sampler != "ddim" or args.ddim_steps:
+        wl["label"] += f" [variant: {args.sampler.upper()}-{wl['ddim_steps']} {wl['schedule']}]"
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -202,6 +210,9 @@ def main():
     torch.cuda.manual_seed(1234 + rank)
 
     def loop(g, k):
+        if args.sampler == "ddpm":
+            return diffusion.p_sample_loop(fn, (B, 3, S, S), model_kwargs={"gt": g, "gt_keep_mask": k}, device=dev,
+                                           use_inpainting_injection=True)
         return diffusion.ddim_sample_loop(fn, (B, 3, S, S), model_kwargs={"gt": g, "gt_keep_mask": k}, device=dev,
                                           eta=0.0, use_inpainting_injection=True)
 
@@ -266,7 +277,7 @@ def main():
 
     pk = peaks()
     line = {
-        "metric": "inpainted 256x256 images/s (DDIM-100)" if S == 256 else "inpainted images/s",
+        "metric": (f"inpainted 256x256 images/s ({args.sampler.upper()}-{T})" if S == 256 else "inpainted images/s"),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
