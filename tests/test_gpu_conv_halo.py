@@ -183,3 +183,53 @@ def test_conv_halo_rejects_unsupported(cuda_lib):
         ops.conv2d(x, wk, None, impl="tc", gn_coef=coef)
     assert cuda_lib.fidm_conv_gn_fusable(8, 8, 8, 1024, 1024, 3, 1) == 0
     assert cuda_lib.fidm_conv_gn_fusable(8, 256, 256, 256, 256, 1, 1) == 0
+    assert cuda_lib.fidm_conv_gn_fusable(8, 256, 256, 256, 192, 3, 1) == 0       # cout % 128 != 0
+    assert cuda_lib.fidm_conv_gn_fusable(8, 256, 256, 256, 16, 3, 1) == 1        # the fp32-NCHW head
+    assert cuda_lib.fidm_conv_gn_fusable(1, 32, 32, 256, 256, 3, 1) == 0         # too few boxes to fill the CTA pairs
+    # argument errors surface as ValueError (negative status through the C ABI), never as a launch
+    x = torch.zeros(1, 16, 16, 64, device="cuda", dtype=torch.bfloat16)
+    wk = torch.zeros(128, 3, 3, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError):          # coefficient row shorter than cin
+        ops.conv2d(x, wk, None, impl="tc", gn_coef=torch.zeros(1, 32, 2, device="cuda"))
+    with pytest.raises(ValueError):          # W % 16 != 0
+        ops.conv2d(torch.zeros(1, 16, 24, 64, device="cuda", dtype=torch.bfloat16), wk, None, impl="tc",
+                   gn_coef=torch.zeros(1, 64, 2, device="cuda"))
+    wh = torch.zeros(16, 3, 3, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError):          # the head variant does not upsample
+        ops.conv2d(torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16), wh, None, impl="tc",
+                   gn_coef=torch.zeros(1, 64, 2, device="cuda"), nchw_out_channels=6, x_half_res=True)
+
+
+def test_reduce_colsum_coeff_entry_matches_two_launches(cuda_lib):
+    """fidm_groupnorm_reduce_colsum_coeff == fidm_groupnorm_reduce_colsum followed by fidm_groupnorm_silu_coeff."""
+    import ctypes as C
+    from fidm_b200 import _lib as L
+    from fidm_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(21)
+    B, H, W, Cn, slots = 3, 32, 32, 256, 16
+    colsum = torch.randn(B, slots, Cn, 2, device=dev, generator=g).abs_() * 50          # partial (sum, sum of squares) rows
+    colsum[..., 1] += colsum[..., 0] ** 2 / (H * W / slots)                             # keep variances positive
+    gamma = 1 + 0.2 * torch.randn(Cn, device=dev, generator=g)
+    beta = 0.2 * torch.randn(Cn, device=dev, generator=g)
+    ss = torch.randn(B, 2 * Cn, device=dev, generator=g) * 0.3
+    x = torch.zeros(B, H, W, Cn, device=dev, dtype=torch.bfloat16)                      # only its shape is used
+    chansum = torch.zeros(B, Cn, 2, device=dev)
+    L.check(cuda_lib.fidm_groupnorm_reduce_colsum(L.ptr(colsum), B, slots, Cn, L.ptr(chansum), Cn, 0, L.stream()), "reduce")
+    want = ops.groupnorm_silu_coeff(x, gamma, beta, scale_shift=ss, chansum=chansum)
+    a = L.GnArgs()
+    a.dtype = a.y_dtype = L.BF16
+    a.batch, a.height, a.width, a.channels, a.groups, a.eps = B, H, W, Cn, 32, 1e-5
+    a.x, a.ld_x = L.ptr(x), Cn
+    a.gamma, a.beta = L.ptr(gamma), L.ptr(beta)
+    a.scale_shift, a.ld_ss = L.ptr(ss), 2 * Cn
+    chansum2 = torch.zeros(B, Cn, 2, device=dev)
+    coef = torch.empty(B, Cn, 2, device=dev)
+    L.check(cuda_lib.fidm_groupnorm_reduce_colsum_coeff(L.ptr(colsum), slots, L.ptr(chansum2), Cn, 0, C.byref(a), L.ptr(coef), Cn,
+                                                        L.stream()), "reduce_coeff")
+    torch.cuda.synchronize()
+    assert torch.equal(chansum, chansum2) and torch.equal(coef, want)
+    a.channels = 768                                                                     # 24 channels per group do not tile 32
+    with pytest.raises(ValueError):
+        L.check(cuda_lib.fidm_groupnorm_reduce_colsum_coeff(L.ptr(colsum), slots, L.ptr(chansum2), 768, 0, C.byref(a), L.ptr(coef),
+                                                            768, L.stream()), "reduce_coeff")
