@@ -188,10 +188,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the JSON line must be the only thing on stdout: NCCL_DEBUG=VERSION (set on some boxes) prints a banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # The JSON line must be the only thing on stdout, but NCCL printf()s its version banner there while the
+        # communicator is created: point fd 1 at stderr for the duration of the (eager) initialisation.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     F._lib.check(F._lib.lib().fidm_device_supported(local), "device")
 
     cfg = F.CONFIGS[wl["cfg"]]
