@@ -12,9 +12,12 @@ cosine schedule, known-region injection on) for `--batch` 256x256 images per GPU
            D2H of the finished images, all inside the timed region.
 `roofline`: the dominant kernel (tcgen05 implicit-GEMM conv, 256->256 @ 256x256) timed alone with CUDA
            events: algorithmic FLOPs per launch / average launch time vs the measured bf16 peak.
-`cpu_baseline`: the CPU oracle (a port of the reference; /root/reference does not travel to the GPU
-           box) timed on the host cores on a bounded sample of the same workload.
-`--impl reference`: the reference's CPU implementation of the path (oracle port), all host threads.
+`cpu_baseline`: the reference's OWN CPU implementation (oracle/_ref: an unmodified, git-ignored copy of its five
+           source files made by __graft_entry__.build(); `kind = "reference"`) timed on the host cores on a bounded
+           sample of the same workload; the restatement in oracle/*.py (`kind = "port"`) if no copy exists.
+`--impl reference`: the same CPU implementation, all host threads, one JSON line.
+`--preset cfg3|cfg4|cfg5`: BASELINE.json configs[2] / [3] / [4] as one reproducible command each (see PRESETS).
+`--global-batch G`: strong scaling -- G images split over the ranks (per-GPU batch G / N).
 """
 import argparse
 import json
@@ -39,6 +42,20 @@ WORKLOADS = {
                               "injection on"),
     "t64": dict(cfg="T64", size=64, ddim_steps=50, schedule="cosine", gflop_per_image_eval=20.03,
                 label="T64 9-ch UNet, 64x64, DDIM-50 cosine, injection on (BASELINE configs[0])"),
+}
+
+
+# BASELINE.json configs[2..4] as one reproducible command each: `python bench.py --preset cfgN` (1 GPU) or under
+# torchrun with --gpus N.  A preset fixes the GLOBAL batch (split over the ranks) -> "scaling": "strong".
+PRESETS = {
+    "cfg3": dict(workload="adm256", sampler="ddpm", ddim_steps=1000, schedule="linear", global_batch=32,
+                 note="BASELINE configs[2]: ADM256 DDPM-1000 linear schedule, batch 32 batch-sharded over the ranks"),
+    "cfg4": dict(workload="adm256", sampler="ddim", ddim_steps=50, schedule="cosine",
+                 sweep=[1, 2, 4, 8, 16, 32, 64, 128, 256],
+                 note="BASELINE configs[3]: ADM256 DDIM-50 cosine, global batch sweep 1-256, procedural masks 5-60 %"),
+    "cfg5": dict(workload="adm256", sampler="ddim", ddim_steps=100, schedule="quadratic", global_batch=64, lora=True,
+                 note="BASELINE configs[4]: ADM256 with LoRA-merged qkv / proj_out weights, DDIM-100 quadratic, batch 64 "
+                      "batch-sharded over the ranks"),
 }
 
 
@@ -98,52 +115,74 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_sample(wl, evals, threads=None):
-    """Time `evals` oracle UNet evaluations + sampler steps at batch 1 on the host; returns
-    (images/s extrapolated to the full loop, seconds per eval+step, cores)."""
+def cpu_reference_sample(wl, evals, threads=None):
+    """Time `evals` reverse steps (known-region injection + UNet evaluation + DDIM/DDPM update) at batch 1 on the host
+    cores.  Runs the reference's own code (oracle/_ref: its GaussianDiffusion.ddim_sample / p_sample driving its
+    DiffusionInpaintingModel) when that copy exists, else the oracle restatement.  Returns (seconds per step, cores,
+    kind)."""
     import fidm_b200 as F
     from fidm_b200.utils.synth import synth_batch, synth_state_dict
-    from oracle import diffusion_oracle as dor
-    from oracle import unet_oracle as uor
+    from oracle import ref_loader
     cores = threads or os.cpu_count()
     torch.set_num_threads(cores)
     cfg = F.CONFIGS[wl["cfg"]]
     sd = synth_state_dict(cfg, seed=0)
     data = synth_batch(1, wl["size"], seed=0)
     gt, keep = data["gt"], data["gt_keep_mask"]
-    tab = dor.Tables(F.get_named_beta_schedule(wl["schedule"], wl["ddim_steps"]))
     shape = (1, 3, wl["size"], wl["size"])
     x = torch.randn(*shape)
+    ddpm = wl.get("sampler", "ddim") == "ddpm"
     times = []
+    ref = ref_loader.load()
+    if ref is not None:
+        model = ref_loader.build_model(cfg, sd)
+        d = ref.create_gaussian_diffusion(steps=wl["ddim_steps"], learn_sigma=True, noise_schedule=wl["schedule"])
+        masked, mask = gt * keep, 1 - keep
+
+        def model_fn(xx, ts, **kw):                      # the closure of test_inp_ddim_100.py:373-385
+            return model(xx, ts, masked_image=masked, mask=mask)
+
+        step = d.p_sample if ddpm else d.ddim_sample
+        with torch.no_grad():
+            for i in range(evals):
+                t = torch.full((1,), wl["ddim_steps"] - 1 - i, dtype=torch.int64)
+                t0 = time.perf_counter()
+                x = step(model_fn, x, t, model_kwargs={"gt": gt, "gt_keep_mask": keep}, use_inpainting_injection=True)["sample"]
+                times.append(time.perf_counter() - t0)
+        return times, cores, "reference"
+    from oracle import diffusion_oracle as dor
+    from oracle import unet_oracle as uor
+    tab = dor.Tables(F.get_named_beta_schedule(wl["schedule"], wl["ddim_steps"]))
     with torch.no_grad():
         for i in range(evals):
             t = wl["ddim_steps"] - 1 - i
             t0 = time.perf_counter()
             x = dor.inject(tab, x, t, gt, keep, torch.randn_like(gt))
             out = uor.inpaint_forward(sd, cfg, x, torch.full((1,), t), gt * keep, 1 - keep)
-            x, _ = dor.ddim_update(tab, out, x, t, torch.randn_like(x))
+            x, _ = (dor.ddpm_update if ddpm else dor.ddim_update)(tab, out, x, t, torch.randn_like(x))
             times.append(time.perf_counter() - t0)
-    return times, cores
+    return times, cores, "port"
 
 
 def run_reference(args, wl):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
-    reference cannot travel to the GPU box), each step = one UNet eval + sampler step at batch 1."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, the unmodified copy that
+    travels with the snapshot; the oracle port if absent), each step = one reverse step at batch 1."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.warmup + args.steps
-    times, cores = cpu_oracle_sample(wl, n)
+    times, cores, kind = cpu_reference_sample(wl, n)
     t = times[args.warmup:]
     sec = sum(t) / len(t)
     value = 1.0 / (sec * wl["ddim_steps"])
-    sample = f"{len(t)} x (UNet eval + injection + DDIM update) at batch 1, extrapolated x{wl['ddim_steps']} steps"
-    line = {"impl": "reference", "metric": "inpainted 256x256 images/s (DDIM-100)" if wl["size"] == 256 else
-            "inpainted images/s", "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+    sample = (f"{len(t)} x one reverse step (injection + UNet eval + update) of the reference's own code at batch 1, "
+              f"extrapolated x{wl['ddim_steps']} steps")
+    line = {"impl": "reference", "metric": (f"inpainted 256x256 images/s ({wl['sampler'].upper()}-{wl['ddim_steps']})"
+                                            if wl["size"] == 256 else "inpainted images/s"), "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "per_gpu_batch": 1},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -165,14 +204,30 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-only", action="store_true", help="only time UNet evaluations (ms per eval)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--preset", default=None, choices=sorted(PRESETS))
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong scaling: this many images split over the ranks (per-GPU batch = G / N)")
+    ap.add_argument("--lora", action="store_true", help="LoRA-merged qkv / proj_out weights (same keys and shapes)")
     args = ap.parse_args()
+    preset = PRESETS.get(args.preset)
+    if preset:
+        args.workload, args.sampler, args.ddim_steps, args.schedule = (preset["workload"], preset["sampler"],
+                                                                        preset["ddim_steps"], preset["schedule"])
+        args.lora = args.lora or preset.get("lora", False)
+        if "global_batch" in preset and args.global_batch is None:
+            args.global_batch = preset["global_batch"]
     wl = dict(WORKLOADS[args.workload])
+    wl["sampler"] = args.sampler
     if args.ddim_steps:
         wl["ddim_steps"] = args.ddim_steps
     if args.schedule:
         wl["schedule"] = args.schedule
     if args.schedule or args.sampler != "ddim" or args.ddim_steps:
         wl["label"] += f" [variant: {args.sampler.upper()}-{wl['ddim_steps']} {wl['schedule']}]"
+    if args.lora:
+        wl["label"] += " [LoRA-merged attention weights]"
+    if preset:
+        wl["label"] = preset["note"]
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -204,13 +259,25 @@ def main():
     F._lib.check(F._lib.lib().fidm_device_supported(local), "device")
 
     cfg = F.CONFIGS[wl["cfg"]]
+    strong = args.global_batch is not None
+    if strong:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not a multiple of {world} ranks")
+        args.batch = args.global_batch // world
     B, S, T = args.batch, wl["size"], wl["ddim_steps"]
     model = F.DiffusionInpaintingModel(F.UNetModel(**dict(cfg, in_channels=3)))
-    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    sd = synth_state_dict(cfg, seed=0)
+    if args.lora:
+        from fidm_b200.utils.synth import merge_lora
+        sd = merge_lora(sd, rank=8, alpha=64.0, seed=0)
+    model.load_state_dict(sd, strict=True)
+    del sd
     model.to(dev)
     model.base_model.set_precision(args.precision)
     fn = F.InpaintingModelFn(model)
     diffusion = F.create_gaussian_diffusion(steps=T, learn_sigma=True, noise_schedule=wl["schedule"])
+    if preset and "sweep" in preset:
+        return run_sweep(args, preset, wl, model, fn, diffusion, dev, world, rank, local)
     data = synth_batch(B, S, seed=100 + rank, device=dev)
     gt, keep = data["gt"], data["gt_keep_mask"]
     host_gt, host_keep = data["gt"].cpu().pin_memory(), data["gt_keep_mask"].cpu().pin_memory()
@@ -288,9 +355,13 @@ def main():
     line = {
         "metric": (f"inpainted 256x256 images/s ({args.sampler.upper()}-{T})" if S == 256 else "inpainted images/s"),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": wl["label"], "per_gpu_batch": B, "global_batch": B * world, "ddim_steps": T,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": args.precision,
+        "dtype_note": ("bf16 residual stream / qkv / attention operands; NORMALIZED conv operands (GroupNorm outputs) and the "
+                       "weights they multiply are fp16 -- same width and tensor rate as bf16, 11-bit mantissa, saturating "
+                       "converts; fp32 accumulation") if args.precision == "bf16" else "FFMA verification mode",
+        "data": "synthetic",
+        "config": {"workload": wl["label"], "preset": args.preset, "per_gpu_batch": B, "global_batch": B * world, "ddim_steps": T,
                    "parallelism": f"batch-sharded x{world}, no collective in the loop, one all_gather of the outputs",
                    "l2": f"no flush: one UNet eval streams {plan.pool.nbytes() / 1e9:.1f}+ GB of activations (>> 126 MB L2)",
                    "cuda_graph": bool(model.base_model.use_cuda_graph)},
@@ -310,12 +381,66 @@ def main():
         line["hbm_kernels"] = hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S)
         if world == 1 and not args.no_cpu_baseline:
             evals = 2 if S == 256 else 5
-            times, cores = cpu_oracle_sample(wl, evals + 1)
+            times, cores, kind = cpu_reference_sample(wl, evals + 1)
             sec = sum(times[1:]) / len(times[1:])
-            line["cpu_baseline"] = {"value": 1.0 / (sec * T), "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"{evals} x (UNet eval + injection + DDIM update) at batch 1 after 1 warm-up, "
-                                              f"extrapolated x{T} steps ({sec:.2f} s per step)"}
+            line["cpu_baseline"] = {"value": 1.0 / (sec * T), "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": f"{evals} x one reverse step (injection + UNet eval + update) at batch 1 after 1 "
+                                              f"warm-up, extrapolated x{T} steps ({sec:.2f} s per step)"}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_sweep(args, preset, wl, model, fn, diffusion, dev, world, rank, local):
+    """--preset cfg4: one full DDIM loop per global batch size of the sweep (per-GPU batch = max(1, G / N); sizes that
+    give the same per-GPU batch as a smaller G are skipped), device-timed, max over ranks."""
+    import torch.distributed as dist
+    from fidm_b200.utils.synth import synth_batch
+    S, T = wl["size"], wl["ddim_steps"]
+    rows, seen = [], set()
+    for G in preset["sweep"]:
+        b = max(1, G // world)
+        if b in seen:
+            continue
+        seen.add(b)
+        data = synth_batch(b, S, seed=100 + rank, device=dev)
+        gt, keep = data["gt"], data["gt_keep_mask"]
+        xin = torch.randn(b, 3, S, S, device=dev)
+        tt = torch.full((b,), T // 2, device=dev)
+        for _ in range(3):                                    # warm-up: plan build, graph capture, clocks
+            fn(xin, tt, gt=gt, gt_keep_mask=keep)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        diffusion.ddim_sample_loop(fn, (b, 3, S, S), model_kwargs={"gt": gt, "gt_keep_mask": keep}, device=dev,
+                                   eta=0.0, use_inpainting_injection=True)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+        hole = float((1 - keep).mean().item())
+        rows.append({"global_batch": b * world, "per_gpu_batch": b, "ms_per_loop": ms, "images_per_s": b * world / (ms / 1e3),
+                     "unet_tflops_per_gpu": wl["gflop_per_image_eval"] * b * T / ms, "mask_hole_fraction_rank0": hole})
+        model.base_model._plans.clear()                       # release this batch size's buffers and graph
+        del data, gt, keep, xin
+        torch.cuda.empty_cache()
+    if rank == 0:
+        pk = peaks()
+        best = max(rows, key=lambda r: r["images_per_s"])
+        for r in rows:
+            r["frac_of_sustained_peak"] = r["unet_tflops_per_gpu"] / pk["bf16_tflops_sustained"]
+        print(json.dumps({"metric": f"inpainted 256x256 images/s (DDIM-{T}), batch sweep", "value": best["images_per_s"],
+                          "unit": "images/s", "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": best["ms_per_loop"],
+                          "higher_is_better": True, "scaling": "sweep", "vs_baseline": None, "dtype": args.precision,
+                          "data": "synthetic", "config": {"workload": wl["label"], "preset": args.preset},
+                          "sweep": rows}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -400,8 +525,11 @@ def dominant_kernel_roofline(ops, dev, pk, B):
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at batch 8 from the committed
             # `ncu --set full` capture (profiles/r1d_ncu_full_conv_halo.txt): 269.7 MB + 238.7 MB; the algorithmic
             # minimum is 268.4 MB in + 268.4 MB out + 1.2 MB of weights
-            "traffic": 508.4e6 * B / 8, "traffic_src": "profiles/r1d_ncu_full_conv_halo.txt",
-            "tensor_pipe_active_pct_ncu": 84.6,
+            # NOT measured in this run: dram bytes of this kernel at batch 8 from the committed `ncu --set full` capture
+            # (profiles/r1d_ncu_full_conv_halo.txt: 269.7 MB read + 238.7 MB written); scaled by batch when it differs
+            "traffic": 508.4e6 * B / 8,
+            "ncu_capture": {"file": "profiles/r1d_ncu_full_conv_halo.txt", "batch": 8, "dram_bytes": 508.4e6,
+                            "tensor_pipe_active_pct": 84.6, "static": True},
             "k1_same_layer_prenormalized_operand": {"ms_per_launch": ms_k1, "achieved": flops / (ms_k1 * 1e-3) / 1e12}}
 
 

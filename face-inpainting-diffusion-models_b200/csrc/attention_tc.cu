@@ -266,11 +266,8 @@ extern "C" int fidm_attention_qkv_nhwc_bf16(const fidm_attn_args* a, fidm_stream
   // [B][T][3C] viewed as NHWC with H = 1: box = 64 channels x 128 tokens
   if ((rc = make_nhwc_map(&tmQKV, a->qkv, 3 * Cn, a->tokens, 1, a->batch, a->ld_qkv, 128, 1, 1, 0))) return rc;
   if ((rc = make_nhwc_map(&tmO, a->out, Cn, a->tokens, 1, a->batch, a->ld_out, 128, 1, 1, 0))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FIDM_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};      // per (instantiation, device)
+  FIDM_CUDA(ensure_dynamic_smem(attn_tc_kernel, kAttnSmem, attr_set));
   dim3 grid((a->tokens + BQ - 1) / BQ, a->heads, a->batch);
   FIDM_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, tmQKV, tmO, p));
   FIDM_CHECK_LAUNCH("attention_tc");

@@ -39,15 +39,32 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs).
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: set it once per (kernel
+// instantiation, device).  `flags` is a function-local static array of kMaxDevices bools owned by the caller.
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(F kernel, int bytes, bool (&flags)[kMaxDevices]) {
+  const int dev = current_device();
+  if (flags[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) flags[dev] = true;
+  return e;
 }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
@@ -58,7 +75,12 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+// fp16 stores saturate (cvt.satfinite): a normalized operand beyond 65504 clamps instead of becoming inf
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
 
 // A vector of V elements of T, loaded/stored with one instruction when it is 4/8/16 bytes.
 template <typename T, int V> struct alignas(sizeof(T) * V) Vec { T v[V]; };

@@ -526,11 +526,8 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   } else {
     tmY = tmA;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    FIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};      // per (instantiation, device)
+  FIDM_CUDA(ensure_dynamic_smem(conv_tc_kernel<BLOCK_N, CG>, Cfg::kSmemBytes, attr_set));
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   if (split_k > 1) {
     // workspace: the first kSplitCounterBytes hold one int arrival counter per tile (zero on entry and on exit --

@@ -137,7 +137,11 @@ class Weights:
                     conv(n + ".out_layers.3", normalized=True)
                 else:
                     conv(n + ".skip_connection")
-                    conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"), normalized=True)
+                    # the 1x1 skip rides the out_layers conv as extra K slices (Plan._conv, x2): that launch takes the
+                    # tensor-core kernel -- and fp16 normalized operands -- only if the skip source qualifies too
+                    # (the same predicate _conv applies); otherwise it is the SIMT kernel on bf16 operands
+                    conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"),
+                         normalized=layer.skip != "conv1x1" or layer.cin % 64 == 0)
                 w = f32(n + ".emb_layers.1.weight")
                 emb_w.append(w)
                 emb_b.append(f32(n + ".emb_layers.1.bias"))

@@ -150,6 +150,12 @@ class GaussianDiffusion:
         a.coef, a.x = L.ptr(coef), L.ptr(x)
         if t_dev is not None:
             t_dev = t_dev.detach().to(device=x.device, dtype=torch.int64).contiguous()
+            # the kernel indexes the coefficient table with these: validate on the host (the reference raises
+            # IndexError from its table gather, :21).  Only the single-step entry points pass per-sample tensors;
+            # the fused loops pass scalars that the C ABI range-checks itself.
+            lo, hi = (int(v) for v in torch.stack(torch.aminmax(t_dev)).tolist())
+            if lo < (1 if mode == L.STEP_UPDATE_INJECT else 0) or hi >= a.num_timesteps:
+                raise IndexError(f"timesteps [{lo}, {hi}] out of range for a {a.num_timesteps}-step table")
             keepalive.append(t_dev)
             a.t_dev = L.ptr(t_dev)
         if mode != L.STEP_INJECT_ONLY:

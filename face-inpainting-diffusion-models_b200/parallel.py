@@ -43,6 +43,9 @@ def sample_sharded(diffusion, model_fn, gt, gt_keep_mask, *, ddim=True, eta=0.0,
     Per-rank generator seed = seed + rank (parity is checked shard by shard against the oracle)."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
+    if gt.shape[0] < world:
+        # an empty shard would make its rank fail in the loop while the others wait in all_gather
+        raise ValueError(f"batch {gt.shape[0]} < world size {world}: every rank needs at least one image")
     g, k = shard(gt, rank, world), shard(gt_keep_mask, rank, world)
     torch.manual_seed(seed + rank)
     if g.is_cuda:

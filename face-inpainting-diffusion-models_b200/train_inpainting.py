@@ -74,6 +74,14 @@ class InpaintingModelFn:
     def parameters(self):
         return self.model.parameters()
 
+    def eval(self):
+        self.model.eval()
+        return self
+
+    def train(self, mode=True):
+        self.model.train(mode)
+        return self
+
     def __call__(self, x, t, gt=None, gt_keep_mask=None, masked_image=None, mask=None, **kwargs):
         if masked_image is None or mask is None:
             if gt is None or gt_keep_mask is None:

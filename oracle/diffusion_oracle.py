@@ -19,8 +19,8 @@ so the same numbers can be fed to the CUDA path.  `noise_fn=None` draws from tor
 global generator in the reference's order (randn(shape); per step randn_like(gt) on
 cache miss, then randn_like(x)).
 
-Parity status: pinned against the reference itself by `oracle/make_golden.py`
-(bit-exact on the DDIM path, tests/test_oracle_pinned.py); the reference has no tests.
+Parity status: pinned against the reference itself by `oracle/make_golden.py` / `make_golden_r2.py`
+(bit-exact on the DDIM path for every mean / variance type, tests/test_oracle_pinned.py); the reference has no tests.
 """
 import numpy as np
 import torch
@@ -64,33 +64,47 @@ def inject(tab, x, t, gt, keep, noise, cumulative=True):
     return m * wg + (1 - m) * x
 
 
-def mean_variance(tab, out, x, t, var_type="learned_range", clip=True):
-    """p_mean_variance (:213-298) for an EPSILON model; returns mean, log_variance, x0."""
+def mean_variance(tab, out, x, t, var_type="learned_range", clip=True, mean_type="epsilon"):
+    """p_mean_variance (:213-298); returns mean, log_variance, x0.  mean_type: "epsilon" | "start_x" | "previous_x"
+    (ModelMeanType, :273-286); var_type: "learned_range" | "learned" | "fixed_large" | "fixed_small" (:241-265)."""
     C = x.shape[1]
     if var_type == "learned_range":
-        eps, v = torch.split(out, C, dim=1)
+        mo, v = torch.split(out, C, dim=1)
         min_log = _c(tab.posterior_log_variance_clipped, t)
         max_log = _c(np.log(tab.betas), t)
         frac = (v + 1) / 2
         logvar = frac * max_log + (1 - frac) * min_log
+    elif var_type == "learned":
+        mo, logvar = torch.split(out, C, dim=1)
     elif var_type == "fixed_large":
-        eps = out
+        mo = out
         logvar = _c(np.log(np.append(tab.posterior_variance[1], tab.betas[1:])), t).expand(x.shape)
     elif var_type == "fixed_small":
-        eps = out
+        mo = out
         logvar = _c(tab.posterior_log_variance_clipped, t).expand(x.shape)
     else:
         raise NotImplementedError(var_type)
-    x0 = _c(tab.sqrt_recip_alphas_cumprod, t) * x - _c(tab.sqrt_recipm1_alphas_cumprod, t) * eps
-    if clip:
-        x0 = x0.clamp(-1, 1)
+
+    def process(v):
+        return v.clamp(-1, 1) if clip else v
+
+    if mean_type == "previous_x":                      # :274-278, _predict_xstart_from_xprev :307-314
+        x0 = process(_c(1.0 / tab.posterior_mean_coef1, t) * mo
+                     - _c(tab.posterior_mean_coef2 / tab.posterior_mean_coef1, t) * x)
+        return mo, logvar, x0
+    if mean_type == "start_x":
+        x0 = process(mo)
+    elif mean_type == "epsilon":
+        x0 = process(_c(tab.sqrt_recip_alphas_cumprod, t) * x - _c(tab.sqrt_recipm1_alphas_cumprod, t) * mo)
+    else:
+        raise NotImplementedError(mean_type)
     mean = _c(tab.posterior_mean_coef1, t) * x0 + _c(tab.posterior_mean_coef2, t) * x
     return mean, logvar, x0
 
 
-def ddim_update(tab, out, x, t, z, eta=0.0, var_type="learned_range", clip=True):
+def ddim_update(tab, out, x, t, z, eta=0.0, var_type="learned_range", clip=True, mean_type="epsilon"):
     """ddim_sample (:464-485) after the injection."""
-    _, _, x0 = mean_variance(tab, out, x, t, var_type, clip)
+    _, _, x0 = mean_variance(tab, out, x, t, var_type, clip, mean_type)
     eps = (_c(tab.sqrt_recip_alphas_cumprod, t) * x - x0) / _c(tab.sqrt_recipm1_alphas_cumprod, t)
     ab = _c(tab.alphas_cumprod, t)
     abp = _c(tab.alphas_cumprod_prev, t)
@@ -100,16 +114,16 @@ def ddim_update(tab, out, x, t, z, eta=0.0, var_type="learned_range", clip=True)
     return mean_pred + nz * sigma * z, x0
 
 
-def ddpm_update(tab, out, x, t, z, var_type="learned_range", clip=True):
+def ddpm_update(tab, out, x, t, z, var_type="learned_range", clip=True, mean_type="epsilon"):
     """p_sample (:378-388) after the injection."""
-    mean, logvar, x0 = mean_variance(tab, out, x, t, var_type, clip)
+    mean, logvar, x0 = mean_variance(tab, out, x, t, var_type, clip, mean_type)
     nz = torch.tensor(float(t != 0))
     return mean + nz * torch.exp(0.5 * logvar) * z, x0
 
 
 def sample_loop(tab, model, shape, *, ddim=True, eta=0.0, x_T=None, gt=None, keep=None,
                 model_kwargs=None, var_type="learned_range", clip=True, inject_on=True,
-                schedule="all", cumulative=True, noise_fn=None, trace=None):
+                schedule="all", cumulative=True, noise_fn=None, trace=None, mean_type="epsilon", rescale_timesteps=False):
     """ddim_sample_loop / p_sample_loop (:390-445, :487-538).
 
     model(x, t_int64[B], **model_kwargs) -> [B, C or 2C, H, W].
@@ -134,13 +148,15 @@ def sample_loop(tab, model, shape, *, ddim=True, eta=0.0, x_T=None, gt=None, kee
                     n = noise_fn("inject", t) if noise_fn else torch.randn_like(gt)
                 x = inject(tab, x, t, gt, keep, n, cumulative)
         tt = torch.full((shape[0],), t, dtype=torch.int64)
+        if rescale_timesteps:                              # _scale_timesteps (:321-324)
+            tt = tt.float() * (1000.0 / tab.T)
         with torch.no_grad():
             out = model(x, tt, **model_kwargs)
         z = noise_fn("step", t) if noise_fn else torch.randn_like(x)
         if ddim:
-            x, x0 = ddim_update(tab, out, x, t, z, eta, var_type, clip)
+            x, x0 = ddim_update(tab, out, x, t, z, eta, var_type, clip, mean_type)
         else:
-            x, x0 = ddpm_update(tab, out, x, t, z, var_type, clip)
+            x, x0 = ddpm_update(tab, out, x, t, z, var_type, clip, mean_type)
         if trace is not None:
             trace.append({"t": t, "sample": x.clone(), "pred_xstart": x0.clone(), "model_out": out.clone()})
     return x

@@ -78,3 +78,22 @@ def script_draw_order(seq, eta=0.0, ddpm=False):
         if t > 0:
             order.append(("inject", t))
     return order
+
+
+def class_draw_order(T, inject=True, schedule="all", first=True):
+    """RNG draw order of the class path's loops (gaussian_diffusion.py:96-101,146,381,428,478,521) with the
+    high / low gating of :132-135 -- the same function oracle/make_golden_r2.py used."""
+    seq = [("xT", 0)] if first else []
+    for t in range(T - 1, -1, -1):
+        gated = (schedule == "high" and t < T // 2) or (schedule == "low" and t >= T // 2)
+        if inject and not gated:
+            seq.append(("inject", t))
+        seq.append(("step", t))
+    return seq
+
+
+def hole_psnr(a, b, keep):
+    """PSNR over the inpainted (hole) pixels only: the known region is bit-exact by construction and would flatter
+    a whole-image figure."""
+    hole = (keep.expand_as(a) == 0)
+    return psnr(a[hole], b[hole])

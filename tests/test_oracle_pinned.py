@@ -129,3 +129,58 @@ def test_oracle_script_loops_match_reference(golden_dir):
         out = sor.script_ddpm_loop(tab, fn, shape, gt, masks, x_T=seeded_noise("xT", 0, shape, g["seed_noise"]),
                                    noise_fn=lambda kind, t: seeded_noise(kind, t, shape, g["seed_noise"]))
     assert psnr(out, g["final"]) > 60
+
+
+def test_oracle_mean_and_variance_types_bit_exact(golden_dir):
+    """START_X / PREVIOUS_X mean types and LEARNED variance (gaussian_diffusion.py:241-286) against single steps of
+    the unmodified reference (oracle/make_golden_r2.py)."""
+    cases = torch.load(os.path.join(golden_dir, "sampler_steps_modes.pt"))
+    assert len(cases) == 144
+    for c in cases:
+        tab = dor.Tables(get_named_beta_schedule(c["sched"], c["T"]))
+        two = c["var_type"] in ("LEARNED", "LEARNED_RANGE")
+        g = torch.Generator().manual_seed(c["seed"])
+        B, C, H, W = c["sample"].shape
+        t, T = c["t"], c["T"]
+        x = torch.randn(B, C, H, W, generator=g) * (1.0 + t / T)
+        gt = torch.rand(B, C, H, W, generator=g) * 2 - 1
+        keep = (torch.rand(B, 1, H, W, generator=g) > 0.4).float()
+        mo = torch.randn(B, 2 * C if two else C, H, W, generator=g)
+        if c["var_type"] == "LEARNED":
+            mo[:, C:] = mo[:, C:] * 0.5 - 3.0
+        n_inj = torch.randn(B, C, H, W, generator=g)
+        z = torch.randn(B, C, H, W, generator=g)
+        xi = dor.inject(tab, x, t, gt, keep, n_inj)
+        vt, mt = c["var_type"].lower(), c["mean_type"].lower()
+        mean, logvar, x0 = dor.mean_variance(tab, mo, xi, t, vt, c["clip"], mt)
+        assert torch.equal(mean, c["mean"]) and torch.equal(logvar, c["log_variance"]), (mt, vt, t)
+        if c["mode"] == "ddim":
+            s, x0 = dor.ddim_update(tab, mo, xi, t, z, c["eta"], vt, c["clip"], mt)
+        else:
+            s, x0 = dor.ddpm_update(tab, mo, xi, t, z, vt, c["clip"], mt)
+        assert torch.equal(s, c["sample"]) and torch.equal(x0, c["pred_xstart"]), (mt, vt, t, c["mode"])
+
+
+def test_oracle_loop_switches_match_reference(golden_dir):
+    """injection_schedule gating, fresh (non-cumulative) injection noise, predict_xstart and rescale_timesteps through
+    the oracle's loop against T64 loops of the unmodified reference (a subset: each is 20 UNet evaluations at batch 2)."""
+    gold = torch.load(os.path.join(golden_dir, "t64_loop_variants.pt"))
+    meta = gold["_meta"]
+    cfg = CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=meta["seed_weights"])
+    data = synth_batch(meta["batch"], 64, seed=meta["seed_data"])
+    gt, keep = data["gt"], data["gt_keep_mask"]
+    shape = (meta["batch"], 3, 64, 64)
+    torch.set_num_threads(os.cpu_count())
+    for tag, kw in (("ddim_low", dict(ddim=True, schedule="low")),
+                    ("ddpm_fresh_noise", dict(ddim=False, cumulative=False)),
+                    ("ddim_predict_xstart", dict(ddim=True, mean_type="start_x")),
+                    ("ddim_rescale_t", dict(ddim=True, rescale_timesteps=True))):
+        g = gold[tag]
+        seed = g["seed_noise"]
+        tab = dor.Tables(get_named_beta_schedule("cosine", g["T"]))
+        with torch.no_grad():
+            out = dor.sample_loop(tab, lambda x, t, **k: uor.inpaint_forward(sd, cfg, x, t, gt * keep, 1 - keep), shape,
+                                  x_T=seeded_noise("xT", 0, shape, seed), gt=gt, keep=keep,
+                                  noise_fn=lambda kind, t: seeded_noise(kind, t, shape, seed), **kw)
+        assert psnr(out, g["final"]) > 80, (tag, psnr(out, g["final"]))
