@@ -1,0 +1,528 @@
+// K1s: K1h with the operand roles swapped -- for layers whose Cout is NOT a multiple of 256 (the 128-channel layers of
+// REF-FFHQ256, train_inpainting.py:208-224) and for the 6-channel head (unet.py:148-152).
+//
+//   D^T[M = 128 output channels, N = 256 pixels] = sum over taps (r,s) and 64-channel slices of
+//                                                  W[M, (r,s), 64] * act(X)_{r,s}[N, 64]^T
+//
+// Why: a tcgen05.mma with its A operand in shared memory streams the 128 A rows at a fixed pace, so an MMA with
+// N = 128 takes as long as one with N = 256 -- K1h's 128-wide tiles (pixels as M, 128 output channels as N) run at half
+// the tensor rate (profiles/r1c_halo_probe_ref128.txt: MMA issuer busy 78 %, 760-820 TFLOP/s).  Here the WEIGHTS are the
+// A operand (128 rows) and the transformed pixels the B operand (N = 256): every instruction is a full 128 x 256 x 16.
+//
+//   * One CTA per SM (no CTA pair: M = 128 is one CTA's worth), tile = a 16 x 16 box of output pixels of one image.
+//   * Per 64-channel slice ONE TMA box load fetches the 18 x 18 halo tile of the raw bf16 stream; nine transform warps
+//     (thread = 16-byte chunk x halo column x upper/lower half, nine rows each) apply silu(x*A + B) once and write the
+//     three column-shifted copies [18 rows][16 pixels][64 ch] in the K-major 128-byte-swizzled layout.  A halo row of a
+//     copy is two swizzle atoms, so tap (r,s) is the descriptor  copy_s + r * 2048  -- 256 consecutive pixel rows.
+//   * Weights: 3-stage TMA ring of [128 rows][64 ch] tiles (half the L2->SM bytes per MMA cycle of K1h).
+//   * Accumulator in TMEM: lane = output channel, column = pixel; double-buffered (2 x 256 columns = all of TMEM).
+//   * Transposing epilogue (4 warps, thread = output channel): tcgen05.ld gives a thread 32 consecutive pixels of its
+//     channel; bias / timestep row are per-thread scalars; the residual tile is TMA-loaded into the staging buffer and
+//     updated IN PLACE ([pixel][channel] bf16, 128-byte swizzle: a warp's 32 channels of one pixel are 64 contiguous
+//     bytes -> conflict-free 2-byte accesses), then TMA-stored.  The GroupNorm statistics of the output (per-channel
+//     sum / sum of squares of the stored bf16 values) accumulate in registers -- no shared-memory pass.
+//   * Head (kHead): 16 weight rows are loaded (6 valid), fp32 NCHW stores straight from the accumulator -- a thread's
+//     32 pixels are two 64-byte row segments of its channel plane.
+//   * The optional 1x1 skip source (nn.py:184,212) rides the weight ring: per 64-channel slice its weights and two
+//     16 x 8 pixel boxes, consumed by two N = 128 instructions.
+//
+// Warp roles (512 threads): 0-3 epilogue, 4-12 transform, 13 weight-ring producer, 14 MMA issuer + TMEM owner,
+// 15 halo producer.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_host.cuh"
+#include "sm100_primitives.cuh"
+
+namespace fidm {
+using namespace sm100;
+
+struct ConvSwapParams {
+  int B, H, W;
+  int tiles_w, tiles_h;     // 16 x 16 pixel boxes per image
+  int n_blocks;             // ceil(Cout / 128)
+  int kc1, cin1;            // Cin / 64, Cin
+  int kc2;                  // Cin2 / 64 of the optional 1x1 second source
+  const float2* coef; int ld_coef;
+  const float* bias;
+  const float* row_add; int ld_row_add;
+  int has_res;              // residual tile fetched by TMA into the staging buffer
+  float* colsum; int colsum_slots; int cout;
+  float* y_nchw; int cout_valid;
+};
+
+namespace halo_s {
+constexpr int kThreads = 512;
+constexpr int kEpiThreads = 128;
+constexpr int kXfThreads = 288;                        // warps 4-12
+constexpr int kT = 16, kHalo = 18;
+constexpr int kRawBytes = kHalo * kHalo * 128;         // 41472: one halo tile of a 64-channel slice
+constexpr int kRawStride = 41 * 1024;
+constexpr int kCopyBytes = kHalo * 2048;               // [18 rows][16 pixels][128 B]
+constexpr int kRingStageBytes = 16384;                 // [128 rows][128 B] weights, or one 16 x 8 pixel box of the skip source
+constexpr int kRingStages = 3;
+constexpr int kStageBufBytes = 8192;                   // [2 channel halves][32 pixels][128 B]
+constexpr int kOffRaw = 0;
+constexpr int kOffCopy = kOffRaw + kRawStride;
+constexpr int kOffRing = kOffCopy + 3 * kCopyBytes;
+constexpr int kOffStaging = kOffRing + kRingStages * kRingStageBytes;
+constexpr int kOffBars = kOffStaging + 2 * kStageBufBytes;
+constexpr int kSmemBytes = kOffBars + 256 + 1024;
+static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0 && kOffStaging % 1024 == 0, "swizzle-atom alignment");
+static_assert(kRawBytes <= kRawStride, "raw buffer");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+}  // namespace halo_s
+
+__device__ __forceinline__ uint32_t lds_u32x4(uint32_t addr, uint32_t& y, uint32_t& z, uint32_t& w) {
+  uint32_t x;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+  return x;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// silu(x*A + B) of two packed bf16 values -> two packed 16-bit results; see conv_halo.cu (one MUFU op per value,
+// saturating fp16 convert).
+template <bool OUT_F16>
+__device__ __forceinline__ uint32_t act_pair_s(uint32_t raw, float a0, float b0, float a1, float b1) {
+  const float h0 = fmaf(__uint_as_float(raw << 16), a0, b0);
+  const float h1 = fmaf(__uint_as_float(raw & 0xFFFF0000u), a1, b1);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  const float y0 = fmaf(h0, t0, h0), y1 = fmaf(h1, t1, h1);
+  uint32_t o;
+  if (OUT_F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(y1), "f"(y0));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(y1), "f"(y0));
+  }
+  return o;
+}
+
+template <bool OUT_F16, bool kHead>
+__global__ void __launch_bounds__(halo_s::kThreads, 1)
+conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmW,
+                      const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW2,
+                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
+                      const ConvSwapParams p) {
+  using namespace halo_s;
+  constexpr int kWRows = kHead ? 16 : 128;               // weight rows actually loaded (the head has 16, 6 valid)
+  constexpr uint32_t kWBytes = kWRows * 128;
+  constexpr int kTmemCols = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* const raw_buf = smem + kOffRaw;
+  uint8_t* const copy_buf = smem + kOffCopy;
+  uint8_t* const ring = smem + kOffRing;
+  uint8_t* const staging = smem + kOffStaging;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* const raw_full = bars;              // [1]  TMA -> transform
+  uint64_t* const raw_empty = bars + 1;         // [1]  transform -> halo producer
+  uint64_t* const a_full = bars + 2;            // [3]  transform -> MMA issuer
+  uint64_t* const a_empty = bars + 5;           // [3]  MMA commit -> transform
+  uint64_t* const ring_full = bars + 8;         // [kRingStages]
+  uint64_t* const ring_empty = bars + 8 + kRingStages;
+  uint64_t* const tmem_full = bars + 8 + 2 * kRingStages;     // [2]
+  uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
+  uint64_t* const res_bar = tmem_empty + 2;                   // [2]  residual chunk landed in staging buffer b
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int total_units = tiles_img * p.B * p.n_blocks;
+
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmRaw);
+    tma_prefetch_desc(&tmW);
+    if (p.kc2) { tma_prefetch_desc(&tmX2); tma_prefetch_desc(&tmW2); }
+    if (!kHead) tma_prefetch_desc(&tmY);
+    if (!kHead && p.has_res) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == 14) {
+    if (lane == 0) {
+      mbar_init(&raw_full[0], 1); mbar_init(&raw_empty[0], 1);
+      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+      for (int i = 0; i < 2; ++i) mbar_init(&res_bar[i], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp >= 13) {
+    if (warp == 13 && lane == 0) {
+      // ================================================================ weight / skip-source ring producer
+      int stage = 0; uint32_t phase = 0;
+      auto acquire = [&](uint32_t bytes) {
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], bytes);
+      };
+      auto advance = [&]() { if (++stage == kRingStages) { stage = 0; phase ^= 1; } };
+      for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+        const int n_blk = wu % p.n_blocks, tile = wu / p.n_blocks;
+        const int w0 = (tile % p.tiles_w) * kT;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+        const int n0 = tile / tiles_img;
+        const int co0 = n_blk * 128;
+        for (int kc = 0; kc < p.kc1; ++kc)
+          for (int s = 0; s < 3; ++s)
+            for (int r = 0; r < 3; ++r) {
+              acquire(kWBytes);
+              tma_load_2d(&tmW, &ring_full[stage], ring + stage * kRingStageBytes, (r * 3 + s) * p.cin1 + kc * 64, co0);
+              advance();
+            }
+        for (int kc = 0; kc < p.kc2; ++kc) {
+          acquire(kRingStageBytes);
+          tma_load_2d(&tmW2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
+          advance();
+          for (int hb = 0; hb < 2; ++hb) {
+            acquire(kRingStageBytes);
+            tma_load_4d(&tmX2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, w0, h0 + hb * 8, n0);
+            advance();
+          }
+        }
+      }
+    } else if (warp == 15 && lane == 0) {
+      // ================================================================ halo producer: 18 x 18 boxes of the raw stream
+      uint32_t g = 0;
+      for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+        const int tile = wu / p.n_blocks;
+        const int w0 = (tile % p.tiles_w) * kT;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+        const int n0 = tile / tiles_img;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          mbar_wait(&raw_empty[0], (g & 1u) ^ 1u);
+          mbar_expect_tx(&raw_full[0], kRawBytes);
+          tma_load_4d(&tmRaw, &raw_full[0], raw_buf, kc * 64, w0 - 1, h0 - 1, n0);
+        }
+      }
+    } else if (warp == 14 && lane == 0) {
+      // ================================================================ MMA issuer
+      constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(128, 256) : umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_skip = umma_idesc_bf16(128, 128);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t g = 0;
+      const uint32_t copy_addr = smem_u32(copy_buf), ring_addr = smem_u32(ring);
+      for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        uint32_t accum = 0;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(&a_full[s], g & 1u);
+            tc_fence_after();
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&ring_full[stage], phase);
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(ring_addr + stage * kRingStageBytes);          // weights: 128 rows
+              const uint64_t db = umma_desc_sw128(copy_addr + s * kCopyBytes + r * 2048);        // 256 pixel rows
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_main, accum);
+                accum = 1;
+              }
+              umma_commit(&ring_empty[stage]);
+              if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&a_empty[s]);      // copy s may be overwritten once these MMAs have read it
+          }
+        }
+        for (int kc = 0; kc < p.kc2; ++kc) {
+          const int st_w = stage;
+          mbar_wait(&ring_full[stage], phase);
+          tc_fence_after();
+          if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+          const uint64_t da = umma_desc_sw128(ring_addr + st_w * kRingStageBytes);
+          for (int hb = 0; hb < 2; ++hb) {
+            mbar_wait(&ring_full[stage], phase);
+            tc_fence_after();
+            const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem + (uint32_t)(hb * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_skip, 1u);
+            umma_commit(&ring_empty[stage]);
+            if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&ring_empty[st_w]);
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ==================================================================== transform warps (4-12, 288 threads)
+    // Thread = (16-byte chunk j, halo column x, half yh); it owns the halo pixels (x, 9 yh + i), i = 0..8.
+    const int tt = (int)threadIdx.x - kEpiThreads;
+    const int j = tt & 7;
+    const int l36 = tt >> 3;
+    const int x = l36 % kHalo, yh = l36 / kHalo;
+    const uint32_t raw_addr = smem_u32(raw_buf), copy_addr = smem_u32(copy_buf);
+    // halo pixel px = y * 18 + x of the TMA box sits at px * 128, its 16-byte chunks XOR-swizzled by (px & 7)
+    const int px0 = yh * 9 * kHalo + x;
+    const uint32_t raw0 = raw_addr + px0 * 128;
+    const uint32_t j16 = (uint32_t)j << 4;
+    // copy s: halo pixel (x, y) is pixel xx = x - s of row y: atom (xx >> 3), row (xx & 7) of the atom
+    uint32_t so[3];
+    bool in_copy[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x - s;
+      in_copy[s] = (unsigned)xx < 16u;
+      so[s] = copy_addr + s * kCopyBytes + (yh * 9) * 2048 + ((xx >> 3) & 1) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
+    }
+    uint32_t g = 0;
+    for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+      const int tile = wu / p.n_blocks;
+      const int w0 = (tile % p.tiles_w) * kT;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+      const int n0 = tile / tiles_img;
+      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+      // the conv zero-pads the ACTIVATED tensor: halo pixels outside the image are 0 after the activation
+      const bool col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
+      const bool first_out = col_out || (yh == 0 && h0 == 0);                 // i == 0 of the upper half: halo row 0
+      const bool last_out = col_out || (yh == 1 && h0 + kT == p.H);           // i == 8 of the lower half: halo row 17
+      for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+        float4 c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
+        mbar_wait(&raw_full[0], g & 1u);
+        uint4 v[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const uint32_t sw = (uint32_t)((px0 + i * kHalo) & 7) << 4;
+          uint32_t r1, r2, r3;
+          const uint32_t r0 = lds_u32x4(raw0 + i * (kHalo * 128) + (j16 ^ sw), r1, r2, r3);
+          v[i].x = act_pair_s<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+          v[i].y = act_pair_s<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+          v[i].z = act_pair_s<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+          v[i].w = act_pair_s<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+          const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+          if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+          if (in_copy[s]) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sts_u32x4(so[s] + i * 2048, v[i]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(7, kXfThreads);
+          if (tt == 0) {
+            if (s == 0) mbar_arrive(&raw_empty[0]);       // every transform thread has read the halo tile
+            mbar_arrive(&a_full[s]);
+          }
+        }
+      }
+    }
+  } else {
+    // ==================================================================== epilogue (warps 0-3): thread = output channel
+    const int cl = warp * 32 + lane;                   // TMEM lane == channel within the 128-channel block
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const bool issuer = (threadIdx.x == 0);
+    const uint32_t stg = smem_u32(staging);
+    // [pixel q][channel]: half (cl >> 6) of the buffer, row q, 16-byte chunk ((cl & 63) >> 3) ^ (q & 7), byte (cl & 7) * 2
+    const uint32_t st_thr = (uint32_t)(cl >> 6) * 4096u + (uint32_t)(cl & 7) * 2u;
+    const uint32_t ch16 = (uint32_t)((cl & 63) >> 3) << 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t res_phase = 0u;               // bit b: parity of res_bar[b]
+    uint32_t chunk_ctr = 0;
+    for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+      const int n_blk = wu % p.n_blocks, tile = wu / p.n_blocks;
+      const int w0 = (tile % p.tiles_w) * kT;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+      const int n = tile / tiles_img;
+      const int co0 = n_blk * 128;
+      const int c = co0 + cl;
+      const bool c_ok = kHead ? (cl < p.cout_valid) : true;
+      float add0 = 0.0f, add1 = 0.0f;
+      if (c_ok || !kHead) {
+        if (p.bias && c < p.cout) add0 = __ldg(p.bias + c);
+        if (p.row_add && c < p.cout) add1 = __ldg(p.row_add + (long long)n * p.ld_row_add + c);
+      }
+      float s1 = 0.0f, s2 = 0.0f;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * 256);
+#pragma unroll 1
+      for (int chunk = 0; chunk < 8; ++chunk, ++chunk_ctr) {
+        const uint32_t b = chunk_ctr & 1u;
+        const uint32_t sbuf = stg + b * kStageBufBytes;
+        if (!kHead) {
+          // buffer b was last read by the TMA store issued two chunks ago
+          if (issuer) {
+            bulk_wait_group_read<1>();
+            if (p.has_res) {
+              mbar_expect_tx(&res_bar[b], kStageBufBytes);
+              tma_load_4d(&tmRes, &res_bar[b], staging + b * kStageBufBytes, co0, w0, h0 + 2 * chunk, n);
+              tma_load_4d(&tmRes, &res_bar[b], staging + b * kStageBufBytes + 4096, co0 + 64, w0, h0 + 2 * chunk, n);
+            }
+          }
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(t_acc + (uint32_t)(chunk * 32), v);
+        tc_wait_ld();
+        if (chunk == 7) {                      // this warp's last TMEM read of the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if constexpr (kHead) {
+          if (c_ok) {
+            const long long hw = (long long)p.H * p.W;
+            float* o = p.y_nchw + ((long long)n * p.cout_valid + cl) * hw + (long long)(h0 + 2 * chunk) * p.W + w0;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float4 t;
+                t.x = (__uint_as_float(v[rr * 16 + q4 * 4 + 0]) + add0) + add1;
+                t.y = (__uint_as_float(v[rr * 16 + q4 * 4 + 1]) + add0) + add1;
+                t.z = (__uint_as_float(v[rr * 16 + q4 * 4 + 2]) + add0) + add1;
+                t.w = (__uint_as_float(v[rr * 16 + q4 * 4 + 3]) + add0) + add1;
+                *reinterpret_cast<float4*>(o + (long long)rr * p.W + q4 * 4) = t;
+              }
+          }
+        } else {
+          if (p.has_res) {
+            mbar_wait(&res_bar[b], (res_phase >> b) & 1u);
+            res_phase ^= 1u << b;
+          } else {
+            named_bar_sync(1, kEpiThreads);      // the issuer has seen the old store finish reading buffer b
+          }
+          const uint32_t base = sbuf + st_thr;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const uint32_t addr = base + q * 128 + (ch16 ^ (uint32_t)((q & 7) << 4));
+            float val = (__uint_as_float(v[q]) + add0) + add1;
+            if (p.has_res) {
+              uint32_t rv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rv) : "r"(addr));
+              val += __uint_as_float(rv << 16);
+            }
+            const __nv_bfloat16 hb = __float2bfloat16_rn(val);
+            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(hb);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)bits) : "memory");
+            const float rb = __uint_as_float(bits << 16);
+            s1 += rb;
+            s2 = fmaf(rb, rb, s2);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, kEpiThreads);
+          if (issuer) {
+            tma_store_4d(&tmY, staging + b * kStageBufBytes, co0, w0, h0 + 2 * chunk, n);
+            tma_store_4d(&tmY, staging + b * kStageBufBytes + 4096, co0 + 64, w0, h0 + 2 * chunk, n);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (!kHead && p.colsum) {
+        // fused GroupNorm statistics of the OUTPUT: this tile's 256 pixels are one partial row (the three other slots of
+        // the tile -- the slot grid is per 64 pixels, fidm_conv_colsum_slots -- are zero); fixed-order fold later
+        const int slot = (tile % tiles_img) * 4;
+        float2* dst = reinterpret_cast<float2*>(p.colsum) + ((long long)n * p.colsum_slots + slot) * p.cout + c;
+        dst[0] = make_float2(s1, s2);
+        dst[(long long)p.cout] = make_float2(0.0f, 0.0f);
+        dst[2LL * p.cout] = make_float2(0.0f, 0.0f);
+        dst[3LL * p.cout] = make_float2(0.0f, 0.0f);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (!kHead && issuer) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 14) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+bool conv_halo_swap_supported(const fidm_conv_args& a) {
+  using namespace halo_s;
+  if (!(a.ksize == 3 && a.stride == 1 && a.height % kT == 0 && a.width % kT == 0 && a.cin % 64 == 0 && a.cin > 0)) return false;
+  if (a.x_half_res || a.residual_half_res) return false;
+  if (!(a.dtype == FIDM_F16 || a.dtype == FIDM_BF16)) return false;
+  if (a.y_nchw_f32) return a.cout == 16 && !a.x2 && !a.residual && !a.colsum;
+  return a.cout % 128 == 0;
+}
+
+bool conv_halo_swap_preferred(const fidm_conv_args& a) {
+  // FIDM_HALO_SWAP=0: A/B switch back to K1h's 128-wide / 16-wide tiles
+  static const bool on = getenv("FIDM_HALO_SWAP") == nullptr || atoi(getenv("FIDM_HALO_SWAP")) != 0;
+  return on && conv_halo_swap_supported(a) && (a.y_nchw_f32 || a.cout % 256 != 0);
+}
+
+template <bool OUT_F16, bool kHead>
+static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st) {
+  using namespace halo_s;
+  ConvSwapParams p;
+  p.B = a.batch; p.H = a.height; p.W = a.width;
+  p.tiles_w = a.width / kT; p.tiles_h = a.height / kT;
+  p.n_blocks = kHead ? 1 : a.cout / 128;
+  p.kc1 = a.cin / 64; p.cin1 = a.cin;
+  p.kc2 = a.x2 ? a.cin2 / 64 : 0;
+  p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
+  p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
+  p.has_res = (!kHead && a.residual) ? 1 : 0;
+  p.colsum = a.colsum; p.cout = a.cout;
+  p.colsum_slots = p.tiles_w * p.tiles_h * 4;            // == fidm_conv_colsum_slots(H, W): one slot per 64 pixels
+  p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
+
+  CUtensorMap tmRaw, tmW, tmX2, tmW2, tmY, tmRes;
+  int rc;
+  if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHalo, kHalo, 1, 0))) return rc;
+  if ((rc = make_matrix_map(&tmW, a.w, 9 * a.cin, a.cout, 9 * a.cin, kHead ? 16 : 128, OUT_F16 ? 1 : 0))) return rc;
+  if (a.x2) {
+    if ((rc = make_nhwc_map(&tmX2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kT, 8, 1, 0))) return rc;
+    if ((rc = make_matrix_map(&tmW2, a.w2, a.cin2, a.cout, a.cin2, 128, 0))) return rc;
+  } else {
+    tmX2 = tmW; tmW2 = tmW;
+  }
+  if (!kHead) {
+    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kT, 2, 1, 0))) return rc;
+  } else {
+    tmY = tmW;
+  }
+  tmRes = tmW;
+  if (p.has_res) {
+    if ((rc = make_nhwc_map(&tmRes, a.residual, a.cout, a.width, a.height, a.batch, a.ld_res, kT, 2, 1, 0))) return rc;
+  }
+  static bool attr_set[kMaxDevices] = {};
+  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead>, kSmemBytes, attr_set));
+  const int units = p.tiles_w * p.tiles_h * p.B * p.n_blocks;
+  const int sms = num_sms();
+  const int grid = units < sms ? units : sms;
+  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
+                       tmW2, tmY, tmRes, p));
+  FIDM_CHECK_LAUNCH("conv_halo_swap");
+  return 0;
+}
+
+int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st) {
+  FIDM_REQUIRE(conv_halo_swap_supported(a), FIDM_E_SHAPE,
+               "conv (fused GroupNorm operand, swapped roles): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, "
+               "cout %% 128 == 0 (or the 16-wide fp32-NCHW head), full-resolution input and residual");
+  const bool f16 = a.dtype == FIDM_F16;
+  if (a.y_nchw_f32) return f16 ? launch_conv_halo_swap_t<true, true>(a, st) : launch_conv_halo_swap_t<false, true>(a, st);
+  return f16 ? launch_conv_halo_swap_t<true, false>(a, st) : launch_conv_halo_swap_t<false, false>(a, st);
+}
+
+}  // namespace fidm

@@ -18,4 +18,10 @@ int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld
 bool conv_halo_supported(const fidm_conv_args& a);
 int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st);
 
+// K1s (conv_halo_swap.cu): the same fused operand path with the operand roles swapped (weights = A operand, 256 pixels
+// = N) for Cout % 256 != 0 and the 6-channel head, where K1h's narrow-N tiles run at half the tensor rate.
+bool conv_halo_swap_supported(const fidm_conv_args& a);
+bool conv_halo_swap_preferred(const fidm_conv_args& a);     // supported AND the better kernel for this shape
+int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st);
+
 }  // namespace fidm

@@ -565,12 +565,17 @@ extern "C" int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width
   a.dtype = FIDM_F16; a.batch = batch; a.height = height; a.width = width;
   a.cin = cin; a.cout = cout; a.ksize = ksize; a.stride = stride;
   a.y_nchw_f32 = cout == 16;        // the 16-wide variant is the fp32-NCHW head
+  // FIDM_HALO_MIN_FILL: percent of the CTA pairs (K1s: of the SMs) that must have a unit (default 75)
+  static const int min_fill = getenv("FIDM_HALO_MIN_FILL") ? atoi(getenv("FIDM_HALO_MIN_FILL")) : 75;
+  if (fidm::conv_halo_swap_preferred(a)) {
+    // K1s: one 16 x 16 pixel box x 128 output channels per SM
+    const long long units = (long long)batch * (height / 16) * (width / 16) * (cout == 16 ? 1 : cout / 128);
+    return units * 100 >= (long long)fidm::num_sms() * min_fill ? 1 : 0;
+  }
   if (!fidm::conv_halo_supported(a)) return 0;
   // worth it only when the CTA pairs of the machine are (nearly) all busy: 8 x 16 pixel boxes, two per pair
   const long long units = (long long)batch * (height / 16) * (width / 16) *
                           (cout == 16 ? 1 : cout / (cout % 256 == 0 ? 256 : 128));
-  // FIDM_HALO_MIN_FILL: percent of the CTA pairs that must have a unit (default 75)
-  static const int min_fill = getenv("FIDM_HALO_MIN_FILL") ? atoi(getenv("FIDM_HALO_MIN_FILL")) : 75;
   return units * 100 >= (long long)(fidm::num_sms() / 2) * min_fill ? 1 : 0;
 }
 

@@ -123,6 +123,11 @@ def test_t64_loop_switches_match_reference(cuda_lib, golden_dir, precision, min_
     shape = (meta["batch"], 3, 64, 64)
     worst = {}
     for tag, ddim, dkw, lkw, schedule, och in _VARIANTS:
+        if tag == "ddim_noclip" and precision == "bf16":
+            # without the clamp a random-init net's x0 prediction at t ~ T is sqrt(1/ab - 1) ~ 1e2 x eps and the loop is
+            # chaotic: not a PSNR-comparable image.  clip_denoised=False is pinned bit-exactly at step level
+            # (test_step_mean_and_variance_types_match_reference) and through the fp32-mode loop here.
+            continue
         g = gold[tag]
         T = g["T"]
         d = F.create_gaussian_diffusion(**dict(dict(steps=T, learn_sigma=True, noise_schedule="cosine"), **dkw))
