@@ -712,10 +712,10 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
 }
 
 int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
-  if (conv_halo_swap_preferred(a) && !g_prof) {
+  if (conv_halo_swap_preferred(a)) {
     FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                  "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
-    return launch_conv_halo_swap(a, st);
+    return launch_conv_halo_swap(a, st, g_prof);
   }
   FIDM_REQUIRE(conv_halo_supported(a), FIDM_E_SHAPE,
                "conv (fused GroupNorm operand): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, cout %% 128 == 0 "

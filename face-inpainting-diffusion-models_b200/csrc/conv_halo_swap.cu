@@ -14,20 +14,22 @@
 //     (thread = 16-byte chunk x halo column x upper/lower half, nine rows each) apply silu(x*A + B) once and write the
 //     three column-shifted copies [18 rows][16 pixels][64 ch] in the K-major 128-byte-swizzled layout.  A halo row of a
 //     copy is two swizzle atoms, so tap (r,s) is the descriptor  copy_s + r * 2048  -- 256 consecutive pixel rows.
-//   * Weights: 3-stage TMA ring of [128 rows][64 ch] tiles (half the L2->SM bytes per MMA cycle of K1h).
+//     The warps never synchronise with each other (each arrives on the mbarriers itself); the coefficients of the
+//     current image sit in shared memory.
+//   * Weights: 4-stage TMA ring of [128 rows][64 ch] tiles (half the L2->SM bytes per MMA cycle of K1h).
 //   * Accumulator in TMEM: lane = output channel, column = pixel; double-buffered (2 x 256 columns = all of TMEM).
-//   * Transposing epilogue (4 warps, thread = output channel): tcgen05.ld gives a thread 32 consecutive pixels of its
-//     channel; bias / timestep row are per-thread scalars; the residual tile is TMA-loaded into the staging buffer and
-//     updated IN PLACE ([pixel][channel] bf16, 128-byte swizzle: a warp's 32 channels of one pixel are 64 contiguous
-//     bytes -> conflict-free 2-byte accesses), then TMA-stored.  The GroupNorm statistics of the output (per-channel
-//     sum / sum of squares of the stored bf16 values) accumulate in registers -- no shared-memory pass.
+//   * Epilogue (2 x 4 warps, thread = output channel): tcgen05.ld gives a thread 16 consecutive pixels of its channel;
+//     bias / timestep row are per-thread scalars; a warp's 32 channels of one pixel are 64 contiguous bytes of the NHWC
+//     output, so results are stored (and the residual loaded) with 2-byte accesses straight from registers -- no
+//     shared-memory transpose, no proxy fence.  The GroupNorm statistics of the output (per-channel sum / sum of squares
+//     of the stored bf16 values) accumulate in registers.
 //   * Head (kHead): 16 weight rows are loaded (6 valid), fp32 NCHW stores straight from the accumulator -- a thread's
-//     32 pixels are two 64-byte row segments of its channel plane.
+//     16 pixels are one 64-byte row segment of its channel plane.
 //   * The optional 1x1 skip source (nn.py:184,212) rides the weight ring: per 64-channel slice its weights and two
 //     16 x 8 pixel boxes, consumed by two N = 128 instructions.
 //
-// Warp roles (512 threads): 0-3 epilogue, 4-12 transform, 13 weight-ring producer, 14 MMA issuer + TMEM owner,
-// 15 halo producer.
+// Warp roles (640 threads, 96 registers): 0-7 epilogue (two warpgroups), 8-16 transform, 17 weight-ring producer,
+// 18 MMA issuer + TMEM owner, 19 halo producer.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -47,29 +49,34 @@ struct ConvSwapParams {
   const float2* coef; int ld_coef;
   const float* bias;
   const float* row_add; int ld_row_add;
-  int has_res;              // residual tile fetched by TMA into the staging buffer
+  const unsigned short* residual; int ld_res;   // optional bf16 NHWC at output resolution
+  unsigned short* y; int ld_y;                  // bf16 NHWC output (a channel slice of a wider buffer when ld_y > cout)
   float* colsum; int colsum_slots; int cout;
   float* y_nchw; int cout_valid;
+  unsigned long long* prof;   // PROF instantiation only (tools/halo_probe.py): [CTA][16] cycle counters, layout as K1h
 };
 
+#define PF_T0() do { if constexpr (PROF) pf_t = clock64(); } while (0)
+#define PF_ADD(x) do { if constexpr (PROF) (x) += clock64() - pf_t; } while (0)
+
 namespace halo_s {
-constexpr int kThreads = 512;
-constexpr int kEpiThreads = 128;
-constexpr int kXfThreads = 288;                        // warps 4-12
+constexpr int kThreads = 640;
+constexpr int kEpiThreads = 128;                       // per epilogue warpgroup (warps 0-3, 4-7)
+constexpr int kXfThreads = 288;                        // warps 8-16
 constexpr int kT = 16, kHalo = 18;
 constexpr int kRawBytes = kHalo * kHalo * 128;         // 41472: one halo tile of a 64-channel slice
 constexpr int kRawStride = 41 * 1024;
 constexpr int kCopyBytes = kHalo * 2048;               // [18 rows][16 pixels][128 B]
 constexpr int kRingStageBytes = 16384;                 // [128 rows][128 B] weights, or one 16 x 8 pixel box of the skip source
-constexpr int kRingStages = 3;
-constexpr int kStageBufBytes = 8192;                   // [2 channel halves][32 pixels][128 B]
+constexpr int kRingStages = 4;
 constexpr int kOffRaw = 0;
 constexpr int kOffCopy = kOffRaw + kRawStride;
 constexpr int kOffRing = kOffCopy + 3 * kCopyBytes;
-constexpr int kOffStaging = kOffRing + kRingStages * kRingStageBytes;
-constexpr int kOffBars = kOffStaging + 2 * kStageBufBytes;
+constexpr int kMaxCin = 1024;                          // the coefficient table of one image lives in shared memory
+constexpr int kOffCoef = kOffRing + kRingStages * kRingStageBytes;
+constexpr int kOffBars = kOffCoef + kMaxCin * 8;
 constexpr int kSmemBytes = kOffBars + 256 + 1024;
-static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0 && kOffStaging % 1024 == 0, "swizzle-atom alignment");
+static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0, "swizzle-atom alignment");
 static_assert(kRawBytes <= kRawStride, "raw buffer");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 }  // namespace halo_s
@@ -101,11 +108,10 @@ __device__ __forceinline__ uint32_t act_pair_s(uint32_t raw, float a0, float b0,
   return o;
 }
 
-template <bool OUT_F16, bool kHead>
+template <bool OUT_F16, bool kHead, bool PROF>
 __global__ void __launch_bounds__(halo_s::kThreads, 1)
 conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW2,
-                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
                       const ConvSwapParams p) {
   using namespace halo_s;
   constexpr int kWRows = kHead ? 16 : 128;               // weight rows actually loaded (the head has 16, 6 valid)
@@ -117,7 +123,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
   uint8_t* const raw_buf = smem + kOffRaw;
   uint8_t* const copy_buf = smem + kOffCopy;
   uint8_t* const ring = smem + kOffRing;
-  uint8_t* const staging = smem + kOffStaging;
+  uint8_t* const coef_tab = smem + kOffCoef;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* const raw_full = bars;              // [1]  TMA -> transform
   uint64_t* const raw_empty = bars + 1;         // [1]  transform -> halo producer
@@ -127,27 +133,23 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
   uint64_t* const ring_empty = bars + 8 + kRingStages;
   uint64_t* const tmem_full = bars + 8 + 2 * kRingStages;     // [2]
   uint64_t* const tmem_empty = tmem_full + 2;                 // [2]
-  uint64_t* const res_bar = tmem_empty + 2;                   // [2]  residual chunk landed in staging buffer b
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_img = p.tiles_w * p.tiles_h;
   const int total_units = tiles_img * p.B * p.n_blocks;
 
-  if (warp == 13 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     tma_prefetch_desc(&tmRaw);
     tma_prefetch_desc(&tmW);
     if (p.kc2) { tma_prefetch_desc(&tmX2); tma_prefetch_desc(&tmW2); }
-    if (!kHead) tma_prefetch_desc(&tmY);
-    if (!kHead && p.has_res) tma_prefetch_desc(&tmRes);
   }
-  if (warp == 14) {
+  if (warp == 18) {
     if (lane == 0) {
-      mbar_init(&raw_full[0], 1); mbar_init(&raw_empty[0], 1);
-      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+      mbar_init(&raw_full[0], 1); mbar_init(&raw_empty[0], kXfThreads / 32);
+      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], kXfThreads / 32); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
-      for (int i = 0; i < 2; ++i) mbar_init(&res_bar[i], 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -161,8 +163,8 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
   pdl_wait();
   pdl_trigger();
 
-  if (warp >= 13) {
-    if (warp == 13 && lane == 0) {
+  if (warp >= 17) {
+    if (warp == 17 && lane == 0) {
       // ================================================================ weight / skip-source ring producer
       int stage = 0; uint32_t phase = 0;
       auto acquire = [&](uint32_t bytes) {
@@ -194,7 +196,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
           }
         }
       }
-    } else if (warp == 15 && lane == 0) {
+    } else if (warp == 19 && lane == 0) {
       // ================================================================ halo producer: 18 x 18 boxes of the raw stream
       uint32_t g = 0;
       for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
@@ -208,7 +210,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
           tma_load_4d(&tmRaw, &raw_full[0], raw_buf, kc * 64, w0 - 1, h0 - 1, n0);
         }
       }
-    } else if (warp == 14 && lane == 0) {
+    } else if (warp == 18 && lane == 0) {
       // ================================================================ MMA issuer
       constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(128, 256) : umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc_skip = umma_idesc_bf16(128, 128);
@@ -216,17 +218,25 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t g = 0;
       const uint32_t copy_addr = smem_u32(copy_buf), ring_addr = smem_u32(ring);
+      long long pf_tmem = 0, pf_a = 0, pf_ring = 0, pf_t = 0;
+      const long long pf_start = PROF ? clock64() : 0;
       for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+        PF_T0();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        PF_ADD(pf_tmem);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         uint32_t accum = 0;
         for (int kc = 0; kc < p.kc1; ++kc, ++g) {
           for (int s = 0; s < 3; ++s) {
+            PF_T0();
             mbar_wait(&a_full[s], g & 1u);
+            PF_ADD(pf_a);
             tc_fence_after();
             for (int r = 0; r < 3; ++r) {
+              PF_T0();
               mbar_wait(&ring_full[stage], phase);
+              PF_ADD(pf_ring);
               tc_fence_after();
               const uint64_t da = umma_desc_sw128(ring_addr + stage * kRingStageBytes);          // weights: 128 rows
               const uint64_t db = umma_desc_sw128(copy_addr + s * kCopyBytes + r * 2048);        // 256 pixel rows
@@ -262,11 +272,15 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (PROF && p.prof) {
+        unsigned long long* o = p.prof + 16 * blockIdx.x;
+        o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_tmem; o[2] = pf_a; o[3] = pf_ring;
+      }
     }
-  } else if (warp >= 4) {
-    // ==================================================================== transform warps (4-12, 288 threads)
+  } else if (warp >= 8) {
+    // ==================================================================== transform warps (8-16, 288 threads)
     // Thread = (16-byte chunk j, halo column x, half yh); it owns the halo pixels (x, 9 yh + i), i = 0..8.
-    const int tt = (int)threadIdx.x - kEpiThreads;
+    const int tt = (int)threadIdx.x - 2 * kEpiThreads;
     const int j = tt & 7;
     const int l36 = tt >> 3;
     const int x = l36 % kHalo, yh = l36 / kHalo;
@@ -284,22 +298,44 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
       in_copy[s] = (unsigned)xx < 16u;
       so[s] = copy_addr + s * kCopyBytes + (yh * 9) * 2048 + ((xx >> 3) & 1) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
     }
+    const uint32_t coef_s = smem_u32(coef_tab) + (uint32_t)j * 64u;      // 8 channels x (A/2, B/2) per 16-byte chunk j
+    int coef_n = -1;
     uint32_t g = 0;
+    long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t = 0;
+    const long long pf_start = PROF ? clock64() : 0;
     for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
       const int tile = wu / p.n_blocks;
       const int w0 = (tile % p.tiles_w) * kT;
       const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
       const int n0 = tile / tiles_img;
-      const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef + j * 8);
+      if (n0 != coef_n) {
+        // per-(image, channel) coefficients of this image -> shared memory (once per image: tiles of an image are
+        // consecutive); the barriers keep warps that still read the old table apart from the copy
+        named_bar_sync(7, kXfThreads);
+        const float4* src = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef);
+        for (int i = tt; i < p.cin1 / 2; i += kXfThreads) {
+          const float4 t = __ldg(src + i);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(coef_tab) + (uint32_t)i * 16u), "f"(t.x), "f"(t.y),
+                       "f"(t.z), "f"(t.w) : "memory");
+        }
+        named_bar_sync(7, kXfThreads);
+        coef_n = n0;
+      }
       // the conv zero-pads the ACTIVATED tensor: halo pixels outside the image are 0 after the activation
       const bool col_out = (unsigned)(w0 - 1 + x) >= (unsigned)p.W;
       const bool first_out = col_out || (yh == 0 && h0 == 0);                 // i == 0 of the upper half: halo row 0
       const bool last_out = col_out || (yh == 1 && h0 + kT == p.H);           // i == 8 of the lower half: halo row 17
       for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+        PF_T0();
+        mbar_wait(&raw_full[0], g & 1u);
+        PF_ADD(pf_raw);
+        PF_T0();
         float4 c[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[q] = __ldg(cf + kc * 32 + q);      // (A/2, B/2) of channels 2q, 2q+1 of this chunk
-        mbar_wait(&raw_full[0], g & 1u);
+        for (int q = 0; q < 4; ++q) {      // (A/2, B/2) of channels 2q, 2q+1 of this chunk, from the shared-memory table
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[q].x), "=f"(c[q].y), "=f"(c[q].z), "=f"(c[q].w)
+                       : "r"(coef_s + (uint32_t)(kc * 512 + q * 16)));
+        }
         uint4 v[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -313,70 +349,89 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
           const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
           if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
         }
+        PF_ADD(pf_work);
+        // The transform warps never synchronise with each other: every warp arrives on the mbarriers itself (count 9).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[0]);        // this warp has read its part of the halo tile
+        // copy 0 is published on its own (the MMAs of this slice start with it); copies 1 and 2 share one proxy fence:
+        // copy 1 is not needed before the three taps of copy 0 have been issued
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
+          PF_T0();
           mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+          PF_ADD(pf_ae);
           if (in_copy[s]) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) sts_u32x4(so[s] + i * 2048, v[i]);
           }
-          fence_proxy_async_smem();
-          named_bar_sync(7, kXfThreads);
-          if (tt == 0) {
-            if (s == 0) mbar_arrive(&raw_empty[0]);       // every transform thread has read the halo tile
-            mbar_arrive(&a_full[s]);
+          if (s != 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (s == 2) mbar_arrive(&a_full[1]);
+              mbar_arrive(&a_full[s]);
+            }
           }
         }
       }
     }
+    if (PROF && p.prof && tt == 0) {
+      unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
+      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
+    }
   } else {
-    // ==================================================================== epilogue (warps 0-3): thread = output channel
-    const int cl = warp * 32 + lane;                   // TMEM lane == channel within the 128-channel block
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const bool issuer = (threadIdx.x == 0);
-    const uint32_t stg = smem_u32(staging);
-    // [pixel q][channel]: half (cl >> 6) of the buffer, row q, 16-byte chunk ((cl & 63) >> 3) ^ (q & 7), byte (cl & 7) * 2
-    const uint32_t st_thr = (uint32_t)(cl >> 6) * 4096u + (uint32_t)(cl & 7) * 2u;
-    const uint32_t ch16 = (uint32_t)((cl & 63) >> 3) << 4;
+    // ==================================================================== epilogue (warps 0-7): thread = output channel
+    // Two warpgroups; warpgroup wg drains pixel columns [128 wg, 128 wg + 128) of the accumulator (box rows 8 wg .. 8 wg + 7)
+    // in eight chunks of one 16-pixel box row.  No shared-memory transpose is needed: a warp holds 32 CONSECUTIVE channels
+    // of one pixel per register index, so a 2-byte store per thread is one fully used 64-byte segment of the NHWC output
+    // (and the residual a 64-byte load).  No staging buffer, no proxy fence, no barrier on this path.
+    // (The first version staged [pixel][channel] tiles in shared memory for TMA stores: its fence.proxy.async -- a
+    // MEMBAR.ALL.CTA that drains every shared store in flight -- and two named barriers per 4 KB chunk made the epilogue
+    // pace the kernel at 15k cycles per tile against 9.2k cycles of MMAs, profiles/r2_k1s_probe.txt.)
+    const int wg = warp >> 2, qw = warp & 3;           // warp qw may only touch TMEM lanes [32 qw, 32 qw + 32)
+    const int cl = qw * 32 + lane;                     // TMEM lane == channel within the 128-channel block
+    const uint32_t lane_sel = (uint32_t)(qw * 32) << 16;
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t res_phase = 0u;               // bit b: parity of res_bar[b]
-    uint32_t chunk_ctr = 0;
+    long long pf_full = 0, pf_buf = 0, pf_ld = 0, pf_t = 0;
+    const long long pf_start = PROF ? clock64() : 0;
     for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
       const int n_blk = wu % p.n_blocks, tile = wu / p.n_blocks;
       const int w0 = (tile % p.tiles_w) * kT;
-      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT + wg * 8;       // this warpgroup's first box row
       const int n = tile / tiles_img;
       const int co0 = n_blk * 128;
       const int c = co0 + cl;
       const bool c_ok = kHead ? (cl < p.cout_valid) : true;
-      float add0 = 0.0f, add1 = 0.0f;
-      if (c_ok || !kHead) {
-        if (p.bias && c < p.cout) add0 = __ldg(p.bias + c);
-        if (p.row_add && c < p.cout) add1 = __ldg(p.row_add + (long long)n * p.ld_row_add + c);
+      float add = 0.0f;
+      if (c < p.cout) {
+        if (p.bias) add = __ldg(p.bias + c);
+        if (p.row_add) add += __ldg(p.row_add + (long long)n * p.ld_row_add + c);
       }
-      float s1 = 0.0f, s2 = 0.0f;
+      float s1a = 0.0f, s1b = 0.0f, s2a = 0.0f, s2b = 0.0f;
+      const long long pix0 = ((long long)n * p.H + h0) * p.W + w0;          // first pixel of this warpgroup's first row
+      const unsigned short* rp = p.residual ? p.residual + pix0 * p.ld_res + c : nullptr;
+      unsigned short* yp = kHead ? nullptr : p.y + pix0 * p.ld_y + c;
 
+      PF_T0();
       mbar_wait(&tmem_full[acc], acc_phase);
+      PF_ADD(pf_full);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * 256);
+      const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * 256 + wg * 128);
 #pragma unroll 1
-      for (int chunk = 0; chunk < 8; ++chunk, ++chunk_ctr) {
-        const uint32_t b = chunk_ctr & 1u;
-        const uint32_t sbuf = stg + b * kStageBufBytes;
-        if (!kHead) {
-          // buffer b was last read by the TMA store issued two chunks ago
-          if (issuer) {
-            bulk_wait_group_read<1>();
-            if (p.has_res) {
-              mbar_expect_tx(&res_bar[b], kStageBufBytes);
-              tma_load_4d(&tmRes, &res_bar[b], staging + b * kStageBufBytes, co0, w0, h0 + 2 * chunk, n);
-              tma_load_4d(&tmRes, &res_bar[b], staging + b * kStageBufBytes + 4096, co0 + 64, w0, h0 + 2 * chunk, n);
-            }
-          }
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        PF_T0();
+        unsigned short rv[16];
+        if (!kHead && rp) {                    // issued before the accumulator read: the loads fly under tcgen05.ld
+          const unsigned short* r0 = rp + (long long)chunk * p.W * p.ld_res;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) rv[q] = __ldg(r0 + (long long)q * p.ld_res);
         }
-        uint32_t v[32];
-        tmem_ld_32x32(t_acc + (uint32_t)(chunk * 32), v);
+        PF_ADD(pf_buf);
+        PF_T0();
+        uint32_t v[16];
+        tmem_ld_32x16(t_acc + (uint32_t)(chunk * 16), v);
         tc_wait_ld();
+        PF_ADD(pf_ld);
         if (chunk == 7) {                      // this warp's last TMEM read of the accumulator
           tc_fence_before();
           __syncwarp();
@@ -385,70 +440,49 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         if constexpr (kHead) {
           if (c_ok) {
             const long long hw = (long long)p.H * p.W;
-            float* o = p.y_nchw + ((long long)n * p.cout_valid + cl) * hw + (long long)(h0 + 2 * chunk) * p.W + w0;
+            float* o = p.y_nchw + ((long long)n * p.cout_valid + cl) * hw + (long long)(h0 + chunk) * p.W + w0;
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                float4 t;
-                t.x = (__uint_as_float(v[rr * 16 + q4 * 4 + 0]) + add0) + add1;
-                t.y = (__uint_as_float(v[rr * 16 + q4 * 4 + 1]) + add0) + add1;
-                t.z = (__uint_as_float(v[rr * 16 + q4 * 4 + 2]) + add0) + add1;
-                t.w = (__uint_as_float(v[rr * 16 + q4 * 4 + 3]) + add0) + add1;
-                *reinterpret_cast<float4*>(o + (long long)rr * p.W + q4 * 4) = t;
-              }
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float4 t;
+              t.x = __uint_as_float(v[q4 * 4 + 0]) + add;
+              t.y = __uint_as_float(v[q4 * 4 + 1]) + add;
+              t.z = __uint_as_float(v[q4 * 4 + 2]) + add;
+              t.w = __uint_as_float(v[q4 * 4 + 3]) + add;
+              *reinterpret_cast<float4*>(o + q4 * 4) = t;
+            }
           }
         } else {
-          if (p.has_res) {
-            mbar_wait(&res_bar[b], (res_phase >> b) & 1u);
-            res_phase ^= 1u << b;
-          } else {
-            named_bar_sync(1, kEpiThreads);      // the issuer has seen the old store finish reading buffer b
-          }
-          const uint32_t base = sbuf + st_thr;
+          unsigned short* y0 = yp + (long long)chunk * p.W * p.ld_y;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const uint32_t addr = base + q * 128 + (ch16 ^ (uint32_t)((q & 7) << 4));
-            float val = (__uint_as_float(v[q]) + add0) + add1;
-            if (p.has_res) {
-              uint32_t rv;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rv) : "r"(addr));
-              val += __uint_as_float(rv << 16);
-            }
-            const __nv_bfloat16 hb = __float2bfloat16_rn(val);
-            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(hb);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)bits) : "memory");
-            const float rb = __uint_as_float(bits << 16);
-            s1 += rb;
-            s2 = fmaf(rb, rb, s2);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(2, kEpiThreads);
-          if (issuer) {
-            tma_store_4d(&tmY, staging + b * kStageBufBytes, co0, w0, h0 + 2 * chunk, n);
-            tma_store_4d(&tmY, staging + b * kStageBufBytes + 4096, co0 + 64, w0, h0 + 2 * chunk, n);
-            bulk_commit_group();
+          for (int q = 0; q < 16; ++q) {
+            float val = __uint_as_float(v[q]) + add;
+            if (rp) val += __uint_as_float((uint32_t)rv[q] << 16);
+            const unsigned short bits = __bfloat16_as_ushort(__float2bfloat16_rn(val));
+            y0[(long long)q * p.ld_y] = bits;
+            const float rb = __uint_as_float((uint32_t)bits << 16);
+            if (q & 1) { s1b += rb; s2b = fmaf(rb, rb, s2b); } else { s1a += rb; s2a = fmaf(rb, rb, s2a); }
           }
         }
       }
       if (!kHead && p.colsum) {
-        // fused GroupNorm statistics of the OUTPUT: this tile's 256 pixels are one partial row (the three other slots of
-        // the tile -- the slot grid is per 64 pixels, fidm_conv_colsum_slots -- are zero); fixed-order fold later
-        const int slot = (tile % tiles_img) * 4;
+        // fused GroupNorm statistics of the OUTPUT: this warpgroup's 128 pixels are one partial row, the next slot of the
+        // pair (the slot grid is per 64 pixels, fidm_conv_colsum_slots) is zero; fixed-order fold later
+        const int slot = (tile % tiles_img) * 4 + wg * 2;
         float2* dst = reinterpret_cast<float2*>(p.colsum) + ((long long)n * p.colsum_slots + slot) * p.cout + c;
-        dst[0] = make_float2(s1, s2);
+        dst[0] = make_float2(s1a + s1b, s2a + s2b);
         dst[(long long)p.cout] = make_float2(0.0f, 0.0f);
-        dst[2LL * p.cout] = make_float2(0.0f, 0.0f);
-        dst[3LL * p.cout] = make_float2(0.0f, 0.0f);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (!kHead && issuer) bulk_wait_group_read<0>();
+    if (PROF && p.prof && threadIdx.x == 0) {
+      unsigned long long* o = p.prof + 16 * blockIdx.x + 8;
+      o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_full; o[2] = pf_buf; o[3] = pf_ld;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 14) {
+  if (warp == 18) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -457,7 +491,8 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
 // ------------------------------------------------------------------------------------------ host
 bool conv_halo_swap_supported(const fidm_conv_args& a) {
   using namespace halo_s;
-  if (!(a.ksize == 3 && a.stride == 1 && a.height % kT == 0 && a.width % kT == 0 && a.cin % 64 == 0 && a.cin > 0)) return false;
+  if (!(a.ksize == 3 && a.stride == 1 && a.height % kT == 0 && a.width % kT == 0 && a.cin % 64 == 0 && a.cin > 0 &&
+        a.cin <= kMaxCin)) return false;
   if (a.x_half_res || a.residual_half_res) return false;
   if (!(a.dtype == FIDM_F16 || a.dtype == FIDM_BF16)) return false;
   if (a.y_nchw_f32) return a.cout == 16 && !a.x2 && !a.residual && !a.colsum;
@@ -470,8 +505,8 @@ bool conv_halo_swap_preferred(const fidm_conv_args& a) {
   return on && conv_halo_swap_supported(a) && (a.y_nchw_f32 || a.cout % 256 != 0);
 }
 
-template <bool OUT_F16, bool kHead>
-static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st) {
+template <bool OUT_F16, bool kHead, bool PROF = false>
+static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof = nullptr) {
   using namespace halo_s;
   ConvSwapParams p;
   p.B = a.batch; p.H = a.height; p.W = a.width;
@@ -481,12 +516,14 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st) {
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
-  p.has_res = (!kHead && a.residual) ? 1 : 0;
+  p.residual = kHead ? nullptr : reinterpret_cast<const unsigned short*>(a.residual); p.ld_res = a.ld_res;
+  p.y = reinterpret_cast<unsigned short*>(a.y); p.ld_y = a.ld_y;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 4;            // == fidm_conv_colsum_slots(H, W): one slot per 64 pixels
   p.y_nchw = a.y_nchw_f32 ? reinterpret_cast<float*>(a.y) : nullptr; p.cout_valid = a.cout_valid;
+  p.prof = PROF ? prof : nullptr;
 
-  CUtensorMap tmRaw, tmW, tmX2, tmW2, tmY, tmRes;
+  CUtensorMap tmRaw, tmW, tmX2, tmW2;
   int rc;
   if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHalo, kHalo, 1, 0))) return rc;
   if ((rc = make_matrix_map(&tmW, a.w, 9 * a.cin, a.cout, 9 * a.cin, kHead ? 16 : 128, OUT_F16 ? 1 : 0))) return rc;
@@ -496,31 +533,23 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st) {
   } else {
     tmX2 = tmW; tmW2 = tmW;
   }
-  if (!kHead) {
-    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, kT, 2, 1, 0))) return rc;
-  } else {
-    tmY = tmW;
-  }
-  tmRes = tmW;
-  if (p.has_res) {
-    if ((rc = make_nhwc_map(&tmRes, a.residual, a.cout, a.width, a.height, a.batch, a.ld_res, kT, 2, 1, 0))) return rc;
-  }
   static bool attr_set[kMaxDevices] = {};
-  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead>, kSmemBytes, attr_set));
+  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead, PROF>, kSmemBytes, attr_set));
   const int units = p.tiles_w * p.tiles_h * p.B * p.n_blocks;
   const int sms = num_sms();
   const int grid = units < sms ? units : sms;
-  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
-                       tmW2, tmY, tmRes, p));
+  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead, PROF>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
+                       tmW2, p));
   FIDM_CHECK_LAUNCH("conv_halo_swap");
   return 0;
 }
 
-int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st) {
+int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof) {
   FIDM_REQUIRE(conv_halo_swap_supported(a), FIDM_E_SHAPE,
                "conv (fused GroupNorm operand, swapped roles): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, "
                "cout %% 128 == 0 (or the 16-wide fp32-NCHW head), full-resolution input and residual");
   const bool f16 = a.dtype == FIDM_F16;
+  if (prof && f16 && !a.y_nchw_f32) return launch_conv_halo_swap_t<true, false, true>(a, st, prof);   // instrumented (probe only)
   if (a.y_nchw_f32) return f16 ? launch_conv_halo_swap_t<true, true>(a, st) : launch_conv_halo_swap_t<false, true>(a, st);
   return f16 ? launch_conv_halo_swap_t<true, false>(a, st) : launch_conv_halo_swap_t<false, false>(a, st);
 }

@@ -22,6 +22,6 @@ int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st);
 // = N) for Cout % 256 != 0 and the 6-channel head, where K1h's narrow-N tiles run at half the tensor rate.
 bool conv_halo_swap_supported(const fidm_conv_args& a);
 bool conv_halo_swap_preferred(const fidm_conv_args& a);     // supported AND the better kernel for this shape
-int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st);
+int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof = nullptr);
 
 }  // namespace fidm

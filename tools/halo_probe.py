@@ -90,14 +90,16 @@ def layer(B, H, W, Cin, Cout, seconds):
     torch.cuda.synchronize()
     L.lib().fidm_conv_set_profile_buffer(None)
     pr = prof.view(148, 16).cpu().double()
-    lead = pr[0::2]
+    swapped = Cout % 256 != 0          # K1s: one CTA per SM, every CTA issues MMAs; epilogue slots: total, wait acc, wait buffer, tcgen05.ld
+    lead = pr if swapped else pr[0::2]
     m = lead.mean(0)
     print(f"   MMA issuer   total {m[0]:9.0f} clk | wait accumulator {m[1] / m[0] * 100:5.1f}%  wait operand copy "
           f"{m[2] / m[0] * 100:5.1f}%  wait weight stage {m[3] / m[0] * 100:5.1f}%")
     t = pr.mean(0)
     print(f"   transform    total {t[4]:9.0f} clk | wait halo tile {t[5] / t[4] * 100:5.1f}%  wait free copy "
           f"{t[6] / t[4] * 100:5.1f}%  load+activate {t[7] / t[4] * 100:5.1f}%")
-    print(f"   epilogue     total {t[8]:9.0f} clk | wait accumulator {t[9] / t[8] * 100:5.1f}%", flush=True)
+    extra = f"  wait staging buffer {t[10] / t[8] * 100:5.1f}%  tcgen05.ld {t[11] / t[8] * 100:5.1f}%" if swapped else ""
+    print(f"   epilogue     total {t[8]:9.0f} clk | wait accumulator {t[9] / t[8] * 100:5.1f}%{extra}", flush=True)
 
 
 secs = float(os.environ.get("PROBE_SECONDS", "2.0"))

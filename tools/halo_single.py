@@ -12,7 +12,9 @@ import fidm_b200 as F  # noqa: F401
 from fidm_b200 import ops
 
 dev = "cuda:0"
-B, H, W, Cin, Cout = 8, 256, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256
+B, H, W = 8, 256, 256
+Cin = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+Cout = int(sys.argv[2]) if len(sys.argv) > 2 else 256          # 128: the swapped-role kernel (conv_halo_swap.cu)
 x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
 w = ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9), torch.float16)
 b = torch.zeros(Cout, device=dev)
