@@ -13,13 +13,11 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "conv_host.cuh"
 #include "sm100_primitives.cuh"
 
 namespace fidm {
 using namespace sm100;
-
-int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
-                  int f16);
 
 struct AttnTcParams {
   int B, T, heads, C;      // C = heads * 64

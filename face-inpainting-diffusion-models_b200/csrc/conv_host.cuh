@@ -8,8 +8,9 @@ namespace fidm {
 
 // NHWC 16-bit tensor [N][H][W][C] (pixel stride ld elements) as a 4-D tiled map with the 128-byte swizzle,
 // box = {64 channels, bw, bh, bn}.
+// pixel_stride 2: the box loads every other pixel in W and H (stride-2 convolution).
 int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
-                  int f16);
+                  int f16, int pixel_stride = 1);
 // Row-major 16-bit matrix [rows][cols] (row stride ld elements) as a 2-D map, box = {64, box_rows}.
 int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows, int f16);
 

@@ -31,7 +31,8 @@ namespace fidm {
 using namespace sm100;
 
 struct ConvTcParams {
-  int B, H, W;             // output == input spatial size (stride 1)
+  int B, H, W;             // OUTPUT spatial size
+  int stride;              // 1, or 2: input is 2H x 2W and tap (r,s) of output pixel (h,w) reads input (2h + r - 1, 2w + s - 1)
   int TW, TH, TN;          // pixel box of one M tile
   int tiles_w, tiles_h, tiles_n;
   int n_blocks;            // Cout / BLOCK_N
@@ -148,10 +149,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = it / p.kc1, kc = it - tap * p.kc1;
             const int r = tap / p.ksize, s = tap - r * p.ksize;
             if (CG == 1) {
-              tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
+              tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 * p.stride + s - pad, h0 * p.stride + r - pad, n0);
               tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
             } else {
-              tma_load_4d_2sm(&tmA, &full_bar[stage], sa, kc * 64, w0 + s - pad, h0 + r - pad, n0);
+              tma_load_4d_2sm(&tmA, &full_bar[stage], sa, kc * 64, w0 * p.stride + s - pad, h0 * p.stride + r - pad, n0);
               tma_load_2d_2sm(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
             }
           } else {
@@ -444,14 +445,18 @@ EncodeTiledFn get_encode_tiled() {
 
 // NHWC bf16 tensor [N][H][W][C] (pixel stride ld elements) as a 4-D map, box = {64, bw, bh, bn}.
 int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bn,
-                  int f16) {
+                  int f16, int pixel_stride) {
   EncodeTiledFn enc = get_encode_tiled();
   FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
   FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // pixel_stride 2 (stride-2 convolution, nn.py:126): the box TRAVERSES 2 bw x 2 bh pixels and loads every other one
+  // (ceil(boxDim / elementStride) = bw x bh pixels land in shared memory)
+  const cuuint32_t ps = (cuuint32_t)pixel_stride;
+  cuuint32_t box[4] = {64, (cuuint32_t)bw * ps, (cuuint32_t)bh * ps, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, ps, ps, 1};
+  FIDM_REQUIRE(box[1] <= 256 && box[2] <= 256, FIDM_E_SHAPE, "tensor map: strided box %ux%u exceeds 256", box[1], box[2]);
   CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -494,10 +499,11 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   using Cfg = ConvCfg<BLOCK_N, CG>;
   ConvTcParams p;
   p.split_k = split_k; p.sk_ws = nullptr; p.sk_cnt = nullptr;
-  p.B = a.batch; p.H = a.height; p.W = a.width;
-  pick_pixel_box(a.width, a.height, &p.TW, &p.TH, &p.TN);
-  FIDM_REQUIRE(p.TN <= 256, FIDM_E_SHAPE, "conv_tc: image %dx%d too small for a 128-pixel tile", a.height, a.width);
-  p.tiles_w = a.width / p.TW; p.tiles_h = a.height / p.TH; p.tiles_n = (a.batch + p.TN - 1) / p.TN;
+  const int Ho = a.height / a.stride, Wo = a.width / a.stride;          // a.height / a.width are the INPUT size
+  p.B = a.batch; p.H = Ho; p.W = Wo; p.stride = a.stride;
+  pick_pixel_box(Wo, Ho, &p.TW, &p.TH, &p.TN);
+  FIDM_REQUIRE(p.TN <= 256, FIDM_E_SHAPE, "conv_tc: image %dx%d too small for a 128-pixel tile", Ho, Wo);
+  p.tiles_w = Wo / p.TW; p.tiles_h = Ho / p.TH; p.tiles_n = (a.batch + p.TN - 1) / p.TN;
   p.n_blocks = a.cout / BLOCK_N;
   p.ksize = a.ksize; p.kc1 = a.cin / 64; p.cin1 = a.cin;
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
@@ -513,16 +519,16 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
   int rc;
-  if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN, f16))) return rc;
+  if ((rc = make_nhwc_map(&tmA, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, p.TW, p.TH, p.TN, f16, a.stride))) return rc;
   if ((rc = make_matrix_map(&tmB, a.w, a.ksize * a.ksize * a.cin, a.cout, a.ksize * a.ksize * a.cin, Cfg::kBRows, f16))) return rc;
   if (a.x2) {
-    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, p.TW, p.TH, p.TN, 0))) return rc;
+    if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, Wo, Ho, a.batch, a.ld_x2, p.TW, p.TH, p.TN, 0))) return rc;
     if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, Cfg::kBRows, 0))) return rc;
   } else {
     tmA2 = tmA; tmB2 = tmB;
   }
   if (!a.y_nchw_f32) {
-    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, a.width, a.height, a.batch, a.ld_y, p.TW, p.TH, p.TN, 0))) return rc;
+    if ((rc = make_nhwc_map(&tmY, a.y, a.cout, Wo, Ho, a.batch, a.ld_y, p.TW, p.TH, p.TN, 0))) return rc;
   } else {
     tmY = tmA;
   }
@@ -583,7 +589,9 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   using namespace fidm;
   FIDM_REQUIRE(a && a->x && a->w && a->y, FIDM_E_BADARG, "conv_tc: null x/w/y");
   FIDM_REQUIRE(a->dtype == FIDM_BF16 || a->dtype == FIDM_F16, FIDM_E_BADARG, "conv_tc: dtype must be bf16 or f16");
-  FIDM_REQUIRE(a->stride == 1 && (a->ksize == 1 || a->ksize == 3), FIDM_E_SHAPE, "conv_tc: only stride 1, ksize 1|3");
+  FIDM_REQUIRE((a->stride == 1 && (a->ksize == 1 || a->ksize == 3)) ||
+               (a->stride == 2 && a->ksize == 3 && a->height % 2 == 0 && a->width % 2 == 0 && !a->gn_coef && !a->x2),
+               FIDM_E_SHAPE, "conv_tc: stride 1 with ksize 1|3, or stride 2 with ksize 3 on an even-sized input");
   FIDM_REQUIRE(a->cin % 64 == 0 && a->cin > 0, FIDM_E_SHAPE, "conv_tc: cin %d must be a multiple of 64", a->cin);
   FIDM_REQUIRE(a->cout % 16 == 0, FIDM_E_SHAPE, "conv_tc: cout %d must be a multiple of 16", a->cout);
   if (a->x2) FIDM_REQUIRE(a->w2 && a->cin2 % 64 == 0 && a->cin2 > 0, FIDM_E_SHAPE, "conv_tc: bad second source");
@@ -602,8 +610,9 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   }
   // Widest N tile that still yields about one tile per SM; narrow tiles for the small low-resolution layers.
   int tw, th, tn;
-  pick_pixel_box(a->width, a->height, &tw, &th, &tn);
-  const long long m_tiles = (long long)(a->width / tw) * (a->height / th) * ((a->batch + tn - 1) / tn);
+  const int Ho = a->height / a->stride, Wo = a->width / a->stride;
+  pick_pixel_box(Wo, Ho, &tw, &th, &tn);
+  const long long m_tiles = (long long)(Wo / tw) * (Ho / th) * ((a->batch + tn - 1) / tn);
   const int want = (num_sms() * 3) / 4;
   static const bool pair_ok = getenv("FIDM_CONV_CTA_PAIR") == nullptr || atoi(getenv("FIDM_CONV_CTA_PAIR")) != 0;
   if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want)

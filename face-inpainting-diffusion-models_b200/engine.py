@@ -75,8 +75,9 @@ HEAD_COUT_PAD = 16
 
 
 def tc_eligible(cin, cout, stride=1, head=False):
-    """Shapes the tcgen05 conv kernel takes (fidm_conv2d_nhwc_bf16)."""
-    return stride == 1 and cin % 64 == 0 and (cout % 64 == 0 or (head and cout == 16))
+    """Shapes the tcgen05 conv kernel takes (fidm_conv2d_nhwc_bf16): stride 1, or the stride-2 3x3 of
+    Downsample(use_conv=True) (nn.py:126) through TMA element strides."""
+    return stride in (1, 2) and cin % 64 == 0 and (cout % 64 == 0 or (head and cout == 16 and stride == 1))
 
 
 class Weights:
@@ -400,7 +401,7 @@ class Plan:
         a.splitk_ws, a.splitk_ws_bytes = L.ptr(self.splitk_ws), self.splitk_ws.numel()
         self.keep.append(a)
         tc_ok = (w.precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
-                 (x2 is None or x2.channels % 64 == 0))
+                 (x2 is None or x2.channels % 64 == 0) and (stride == 1 or (ks == 3 and Ho % 2 == 0 and Wo % 2 == 0)))
         assert tc_ok or (wt.dtype != torch.float16 and gn_coef is None)
         fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
         # Fusing the consumer GroupNorm's statistics into this epilogue pays off where the separate statistics
@@ -409,9 +410,10 @@ class Plan:
         k_total = ks * ks * cin_pad + (x2.channels if x2 is not None else 0)
         if name == "input_blocks.0.0" and os.environ.get("FIDM_STEM_STATS", "1") != "0":
             k_total = 1152      # the stem output feeds TWO GroupNorms (first ResBlock, last skip concat): fuse its statistics
-        slots = self.lib.fidm_conv_colsum_slots(Ho, Wo) if (
+        Hy, Wy = Ho // stride, Wo // stride                      # output resolution (Ho, Wo are the INPUT's for stride 2)
+        slots = self.lib.fidm_conv_colsum_slots(Hy, Wy) if (
             tc_ok and nchw_out is None and stats and self.fuse_stats and cout_pad % 64 == 0 and
-            Ho * Wo >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
+            Hy * Wy >= self.FUSE_MIN_PIXELS and k_total >= 1152) else 0
         if slots > 0:
             n = self.B * slots * cout_pad * 2
             if n not in self.colsum_scratch:

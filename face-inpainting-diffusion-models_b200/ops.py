@@ -164,8 +164,9 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
         y = out if out is not None else torch.empty(n, ho, wo, cout, device=x.device, dtype=ydt)
         a.y, a.ld_y, a.cout_valid = L.ptr(y), _nhwc(y)[4], cout
     if impl == "auto":
-        impl = "tc" if (x.dtype in (torch.bfloat16, torch.float16) and stride == 1 and cin % 64 == 0 and
-                        (cout % 64 == 0 or (nchw_out_channels is not None and cout == 16))) else "simt"
+        impl = "tc" if (x.dtype in (torch.bfloat16, torch.float16) and cin % 64 == 0 and
+                        (stride == 1 or (stride == 2 and ks == 3 and h % 2 == 0 and w % 2 == 0 and x2 is None)) and
+                        (cout % 64 == 0 or (nchw_out_channels is not None and cout == 16 and stride == 1))) else "simt"
     fn = L.lib().fidm_conv2d_nhwc_bf16 if impl == "tc" else L.lib().fidm_conv2d_nhwc_simt
     if impl == "tc":
         global _SPLITK_WS
@@ -174,7 +175,7 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
         a.splitk_ws, a.splitk_ws_bytes = L.ptr(_SPLITK_WS), _SPLITK_WS.numel()
     colsum = None
     if want_chansum:
-        slots = L.lib().fidm_conv_colsum_slots(h, w)
+        slots = L.lib().fidm_conv_colsum_slots(ho, wo)
         assert impl == "tc" and slots > 0 and nchw_out_channels is None
         colsum = torch.empty(n, slots, cout, 2, device=x.device, dtype=torch.float32)
         a.colsum = L.ptr(colsum)

@@ -176,3 +176,22 @@ def test_conv_tc_split_k_layers(cuda_lib, B, H, W, Cin, Cout, Cin2):
     outs = [ops.conv2d(x, wk, b, residual=res, impl="tc", **kw).clone() for _ in range(3)]
     _check(outs[0], _ref(x, w, b, residual=res, x2=x2, w2=w2), "split-K")
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 64, 64, 128, 128), (3, 32, 48, 64, 256),
+                                            (8, 256, 256, 128, 128), (2, 128, 128, 256, 256), (1, 8, 8, 512, 512)])
+def test_conv_tc_stride2(cuda_lib, B, H, W, Cin, Cout):
+    """Downsample(use_conv=True) (nn.py:115-133, :126): 3x3 stride 2 pad 1 on the tensor-core kernel -- the A tile of
+    tap (r,s) is a TMA box that loads every other pixel (element strides 2), out-of-image taps zero-filled."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x, w, b, g = _mk(B, H, W, Cin, Cout, 3, seed=H + Cin + 1)
+    res = torch.randn(B, H // 2, W // 2, Cout, device="cuda", generator=g).bfloat16()
+    y = ops.conv2d(x, ops.repack_weight(w.float()), b, stride=2, residual=res, impl="tc")
+    torch.cuda.synchronize()
+    want = Fn.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1) + res.float().permute(0, 3, 1, 2)
+    assert y.shape == (B, H // 2, W // 2, Cout)
+    _check(y, want, ("stride2", B, H, W, Cin, Cout))
+    # the SIMT kernel (fp32 verification mode / odd shapes) gives the same numbers
+    y2 = ops.conv2d(x, ops.repack_weight(w.float()), b, stride=2, residual=res, impl="simt")
+    _check(y2, want, ("stride2 simt", B, H, W, Cin, Cout))

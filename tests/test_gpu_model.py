@@ -53,6 +53,11 @@ def test_ctor_variants_match_reference(cuda_lib, golden_dir, precision, tol):
         data = synth_batch(2, 32, seed=g["seed_data"], device=DEV)
         out = m(g["x"].to(DEV), g["t"].to(DEV), masked_image=data["masked_image"], mask=data["mask"])
         assert rel_l2(out.cpu(), g["out"]) < tol, (tag, precision)
+        if tag == "plain" and precision == "bf16":
+            # Downsample(use_conv=True) (nn.py:126): the stride-2 3x3 runs on the tensor-core kernel, not on conv_simt
+            plan = m.base_model.plan_for(2, 32, 32)
+            s2 = [fn for fn, args in plan.ops if hasattr(args[0], "_obj") and getattr(args[0]._obj, "stride", 1) == 2]
+            assert s2 and all(fn is plan.lib.fidm_conv2d_nhwc_bf16 for fn in s2), s2
 
 
 @pytest.mark.parametrize("precision,min_psnr", [("fp32", 60.0), ("bf16", 40.0)])
