@@ -30,7 +30,8 @@ class StepArgs(C.Structure):
                 ("num_timesteps", i32), ("t_update", i32), ("t_inject", i32),
                 ("t_dev", vp), ("coef", fp), ("x", fp), ("model_out", fp), ("z", fp), ("gt", fp),
                 ("keep_mask", fp), ("inject_noise", fp), ("sample", fp), ("pred_xstart", fp),
-                ("x_next", fp), ("mean_out", fp), ("logvar_out", fp)]
+                ("x_next", fp), ("mean_out", fp), ("logvar_out", fp),
+                ("stem_out", vp), ("stem_dtype", i32), ("stem_ld", i32), ("t_out", fp), ("t_out_value", C.c_float)]
 
 
 class PackArgs(C.Structure):
@@ -115,7 +116,7 @@ def lib():
                 continue
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.fidm_abi_version() != 2:
+        if handle.fidm_abi_version() != 3:
             raise FidmError("libfidm_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

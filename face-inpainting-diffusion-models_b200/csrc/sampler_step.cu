@@ -141,9 +141,25 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const StepParams p) {
         xn[i] = __fadd_rn(__fmul_rn(m[i], wg), __fmul_rn(__fsub_rn(1.0f, m[i]), smp[i]));
       }
       if (a.x_next) store_vec<float, VEC>(a.x_next + off, xn);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) smp[i] = xn[i];
     } else if (a.x_next) {
       store_vec<float, VEC>(a.x_next + off, smp);
     }
+    // Step-boundary fusion: the next evaluation's stem input (channel c of every pixel of the NHWC network input) and
+    // its timestep are written here -- the same roundings as the pack kernel (layout.cu), so the fused loop is
+    // bit-identical to pack + evaluate.
+    if (a.stem_out) {
+      const long long px = (long long)b * a.hw + (long long)pv * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const long long e = (px + i) * a.stem_ld + c;
+        if (a.stem_dtype == FIDM_F16) reinterpret_cast<__half*>(a.stem_out)[e] = from_f32<__half>(smp[i]);
+        else if (a.stem_dtype == FIDM_BF16) reinterpret_cast<__nv_bfloat16*>(a.stem_out)[e] = from_f32<__nv_bfloat16>(smp[i]);
+        else reinterpret_cast<float*>(a.stem_out)[e] = smp[i];
+      }
+    }
+    if (a.t_out && idx < a.batch) a.t_out[idx] = a.t_out_value;
   }
 }
 
@@ -168,6 +184,9 @@ extern "C" int fidm_sampler_step(const fidm_step_args* a, fidm_stream_t stream) 
     FIDM_REQUIRE(a->t_dev || (a->t_inject >= 0 && a->t_inject < a->num_timesteps), FIDM_E_BADARG,
                  "sampler_step: t_inject %d out of range [0,%d)", a->t_inject, a->num_timesteps);
   }
+  if (a->stem_out)
+    FIDM_REQUIRE(a->stem_ld >= a->channels && (a->stem_dtype == FIDM_F32 || a->stem_dtype == FIDM_BF16 || a->stem_dtype == FIDM_F16),
+                 FIDM_E_BADARG, "sampler_step: stem_out needs stem_ld >= channels and a dtype of F32 | BF16 | F16");
   StepParams p;
   p.a = *a;
   const bool vec4 = (a->hw % 4 == 0) && (((uintptr_t)a->x | (uintptr_t)a->model_out | (uintptr_t)a->z |

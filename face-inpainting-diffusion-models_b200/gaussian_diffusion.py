@@ -16,6 +16,7 @@ Training utilities (`training_losses`, `_vb_terms_bpd`, `:540-637`) are not part
 path and raise NotImplementedError.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -119,7 +120,11 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ K4 launcher
     def _step(self, mode, x, *, t=None, t_inject=None, t_dev=None, model_out=None, z=None, gt=None, keep=None,
               inject_noise=None, ddim=True, eta=0.0, clip=True, cumulative=True, want_sample=False,
-              want_x0=False, want_next=False, want_mean=False, want_logvar=False, script_table=None):
+              want_x0=False, want_next=False, want_mean=False, want_logvar=False, script_table=None,
+              stem=None, t_next=None, next_buf=None):
+        """One K4 launch.  stem = (NHWC network-input tensor, timestep tensor) of an engine plan: the state after this call
+        is also written as the first channels of the stem input and `t_next` into the timestep tensor (step-boundary
+        fusion); next_buf: preallocated fp32 tensor for x_next."""
         L.require_cuda(x, model_out, z, gt, keep, inject_noise)
         B, Cn = x.shape[0], x.shape[1]
         hw = x.numel() // (B * Cn)
@@ -181,8 +186,14 @@ class GaussianDiffusion:
                                  (want_next, "x_next", "x_next"), (want_mean, "mean", "mean_out"),
                                  (want_logvar, "log_variance", "logvar_out")):
             if flag:
-                out[key] = torch.empty_like(x)
+                out[key] = next_buf if (key == "x_next" and next_buf is not None) else torch.empty_like(x)
                 setattr(a, field, L.ptr(out[key]))
+        if stem is not None:
+            x_in, t_in = stem
+            a.stem_out, a.stem_dtype, a.stem_ld = L.ptr(x_in), L.dtype_code(x_in.dtype), x_in.shape[-1]
+            if t_next is not None:
+                a.t_out, a.t_out_value = L.ptr(t_in), float(t_next)
+            keepalive += [x_in, t_in]
         L.check(L.lib().fidm_sampler_step(C.byref(a), L.stream()), "sampler_step")
         return out
 
@@ -427,21 +438,37 @@ class GaussianDiffusion:
         def inj_noise(ts):
             return self._cached_noise(gt, ts) if use_cumulative_noise else torch.randn_like(gt)
 
+        def t_value(ts):      # what the model sees for timestep ts: _scale_timesteps (:321-324), fp32 arithmetic
+            if self.rescale_timesteps:
+                return float(np.float32(ts) * np.float32(1000.0 / self.num_timesteps))
+            return float(ts)
+
         B = shape[0]
         T = self.num_timesteps
-        last = None
+        first = T - 1
+        # Step-boundary fusion: when `model` is this package's model_fn (train_inpainting.InpaintingModelFn around a
+        # DiffusionInpaintingModel), K4 writes the next evaluation's stem channels and timestep itself and reads the
+        # UNet output where the head left it: a step is [graph replay, randn, K4] -- no pack, no copies, no clone.
+        plan = None
+        fused_plan = getattr(model, "fused_plan", None)
+        if fused_plan is not None and os.environ.get("FIDM_FUSED_STEP", "1") != "0":
+            plan = fused_plan(tuple(shape), img, t_value(first), mk)
+        stem = (plan.x_in, plan.t_in) if plan is not None else None
+        bufs = [torch.empty_like(img), torch.empty_like(img)] if plan is not None else None
         with torch.no_grad():
-            first = T - 1
             # injection for the first step happens on x_T itself
             if inject and not self._injection_gated(first, injection_schedule):
                 x = self._step(L.STEP_INJECT_ONLY, img, t_inject=first, gt=gt, keep=keep,
                                inject_noise=inj_noise(first), cumulative=use_cumulative_noise,
-                               want_next=True)["x_next"]
+                               want_next=True, stem=stem, next_buf=bufs[0] if bufs else None)["x_next"]
             else:
                 x = img
-            for i in indices:
-                t = torch.full((B,), i, device=device, dtype=torch.long)
-                model_output = self._call_model(model, x, t, mk)
+            for k, i in enumerate(indices):
+                if plan is not None:
+                    model_output = plan.run()                        # stem input and timestep are already in place
+                else:
+                    t = torch.full((B,), i, device=device, dtype=torch.long)
+                    model_output = self._call_model(model, x, t, mk)
                 z = torch.randn_like(x)                              # RNG order: z_t, then n_{t-1}
                 nxt = i - 1
                 do_inj = inject and nxt >= 0 and not self._injection_gated(nxt, injection_schedule)
@@ -451,11 +478,13 @@ class GaussianDiffusion:
                                gt=gt if do_inj else None, keep=keep if do_inj else None,
                                inject_noise=inj_noise(nxt) if do_inj else None,
                                ddim=ddim, eta=eta, clip=clip_denoised, cumulative=use_cumulative_noise,
-                               want_sample=want_out or not do_inj, want_x0=want_out, want_next=do_inj)
-                x = r["x_next"] if do_inj else r["sample"]
+                               want_sample=want_out or (not do_inj and plan is None), want_x0=want_out,
+                               want_next=do_inj or plan is not None,
+                               stem=stem if nxt >= 0 else None, t_next=t_value(nxt) if nxt >= 0 else None,
+                               next_buf=bufs[(k + 1) & 1] if bufs else None)
+                x = r["x_next"] if (do_inj or plan is not None) else r["sample"]
                 if want_out:
-                    last = {"sample": r["sample"], "pred_xstart": r["pred_xstart"]}
-                    yield last
+                    yield {"sample": r["sample"], "pred_xstart": r["pred_xstart"]}
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                   cond_fn=None, model_kwargs=None, device=None, progress=False,

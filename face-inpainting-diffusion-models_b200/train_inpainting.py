@@ -82,17 +82,39 @@ class InpaintingModelFn:
         self.model.train(mode)
         return self
 
+    def _conditioning(self, gt, gt_keep_mask):
+        # the cache holds references, so identity (not an address that could be recycled) is compared
+        k = self._key
+        if k is None or k[0] is not gt or k[1] is not gt_keep_mask or k[2:] != (gt._version, gt_keep_mask._version):
+            self._cond = (gt * gt_keep_mask + torch.zeros_like(gt) * (1 - gt_keep_mask), 1 - gt_keep_mask)
+            self._key = (gt, gt_keep_mask, gt._version, gt_keep_mask._version)
+        return self._cond
+
     def __call__(self, x, t, gt=None, gt_keep_mask=None, masked_image=None, mask=None, **kwargs):
         if masked_image is None or mask is None:
             if gt is None or gt_keep_mask is None:
                 raise ValueError("Ground truth and mask required for inpainting")
-            # the cache holds references, so identity (not an address that could be recycled) is compared
-            k = self._key
-            if k is None or k[0] is not gt or k[1] is not gt_keep_mask or k[2:] != (gt._version, gt_keep_mask._version):
-                self._cond = (gt * gt_keep_mask + torch.zeros_like(gt) * (1 - gt_keep_mask), 1 - gt_keep_mask)
-                self._key = (gt, gt_keep_mask, gt._version, gt_keep_mask._version)
-            masked_image, mask = self._cond
+            masked_image, mask = self._conditioning(gt, gt_keep_mask)
         return self.model(x, t, masked_image=masked_image, mask=mask)
+
+    def fused_plan(self, shape, x, t_first, model_kwargs):
+        """Step-boundary fusion hook of GaussianDiffusion's loops: pack the loop-invariant conditioning channels
+        (masked image, mask x3: unet.py:199) together with the initial state `x` and timestep into the engine plan's
+        network input ONCE and return the plan; from then on the sampler step kernel writes the three state channels
+        and the timestep itself and `plan.run()` is the whole model call.  None: the caller uses __call__ per step."""
+        mk = model_kwargs or {}
+        gt, keep = mk.get("gt"), mk.get("gt_keep_mask")
+        masked_image, mask = mk.get("masked_image"), mk.get("mask")
+        inner = self.model
+        if not hasattr(inner, "base_model") or not hasattr(inner.base_model, "plan_for") or len(shape) != 4:
+            return None
+        if masked_image is None or mask is None:
+            if gt is None or keep is None:
+                return None
+            masked_image, mask = self._conditioning(gt, keep)
+        if not (x.is_cuda and x.dtype == torch.float32 and tuple(x.shape) == tuple(shape)):
+            return None
+        return inner.fused_plan(x, t_first, masked_image, mask)
 
 
 def sample_with_advanced_inpainting(model, diffusion, masked_images, masks, device, num_steps=50, use_ddim=True,

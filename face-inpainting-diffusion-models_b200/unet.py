@@ -170,6 +170,20 @@ class DiffusionInpaintingModel(nn.Module):
         base_model.invalidate()
         self.eval()
 
+    def fused_plan(self, x, t_value, masked_image, mask):
+        """Pack [x | masked_image | mask x3] and a uniform timestep into the plan's network input and return the plan
+        (see train_inpainting.InpaintingModelFn.fused_plan).  The caller owns the plan's inputs until its loop ends."""
+        n, c, h, w = x.shape
+        if c + masked_image.shape[1] + 3 > 16 or self.base_model.micro_batches > 1:
+            return None
+        base = self.base_model
+        plan = base.plan_for(n, h, w)
+        rep = 3 if mask.shape[1] == 1 else 1
+        srcs = [(t.detach().to(torch.float32).contiguous(), t.shape[1], r)
+                for t, r in ((x, 1), (masked_image, 1), (mask, rep))]
+        plan.load_inputs(srcs, torch.full((n,), float(t_value), device=x.device, dtype=torch.float32))
+        return plan
+
     def forward(self, x, t, masked_image, mask):
         """cat([x, masked_image, mask x3]) -> base UNet (unet.py:197-200); the concat is fused into the
         NCHW->NHWC pack kernel."""

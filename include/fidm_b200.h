@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FIDM_ABI_VERSION 2
+#define FIDM_ABI_VERSION 3
 
 #define FIDM_F32  0
 #define FIDM_BF16 1
@@ -106,6 +106,14 @@ typedef struct fidm_step_args {
   float* x_next;                        /* optional: state after injection (input of next eval) */
   float* mean_out;                      /* optional: posterior mean      ("mean", :286)          */
   float* logvar_out;                    /* optional: model log-variance  ("log_variance", :251)  */
+  /* Step-boundary fusion (the UNet's stem input and timestep are written by THIS kernel, so that no pack / copy
+   * launch sits between two evaluations): the state after this call (x_next's value) is also stored as channels
+   * [0, channels) of every pixel of the NHWC network input `stem_out` (pixel stride stem_ld elements, dtype
+   * stem_dtype = FIDM_F32 | FIDM_BF16 | FIDM_F16; the conditioning channels behind it -- masked image, mask x3:
+   * unet.py:199 -- are constant over the loop and are packed once by the caller), and `t_out[0 .. batch)` is set to
+   * t_out_value (the timestep the NEXT evaluation sees, already rescaled if rescale_timesteps, :321-324). */
+  void* stem_out; int32_t stem_dtype, stem_ld;
+  float* t_out; float t_out_value;
 } fidm_step_args;
 int fidm_sampler_step(const fidm_step_args* a, fidm_stream_t stream);
 

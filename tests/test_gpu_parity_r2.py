@@ -360,3 +360,43 @@ def test_out_of_range_timesteps_raise(cuda_lib):
         with pytest.raises(IndexError):
             d.p_sample(lambda xx, ts, **k: mo, x, torch.tensor(bad, device=DEV))
     d.ddim_sample(lambda xx, ts, **k: mo, x, torch.tensor([0, 49], device=DEV))
+
+
+@pytest.mark.parametrize("ddim,eta,schedule,rescale", [(True, 0.0, "all", False), (True, 0.7, "low", True), (False, 0.0, "high", False),
+                                                        (True, 0.0, "none", False)])
+def test_fused_step_boundary_is_bit_identical(cuda_lib, monkeypatch, ddim, eta, schedule, rescale):
+    """Step-boundary fusion (K4 writes the next evaluation's stem channels and timestep, reads the UNet output in place;
+    no pack / copy / clone launches between evaluations) against the unfused loop (pack kernel + model call per step):
+    every yielded sample and pred_xstart must be bit-identical -- in both precisions of the stem input."""
+    import fidm_b200 as F
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    cfg = F.CONFIGS["T64"]
+    sd = synth_state_dict(cfg, seed=2)
+    data = synth_batch(3, 64, seed=8, device=DEV)
+    gt, keep = data["gt"], data["gt_keep_mask"]
+    T = 12
+    inject = schedule != "none"
+    for precision in ("bf16", "fp32"):
+        m = _model(cfg, sd, precision)
+        fn = F.InpaintingModelFn(m)
+        d = F.create_gaussian_diffusion(steps=T, learn_sigma=True, noise_schedule="cosine", rescale_timesteps=rescale)
+        runs = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("FIDM_FUSED_STEP", fused)
+            kw = dict(model_kwargs={"gt": gt, "gt_keep_mask": keep}, device=DEV, use_inpainting_injection=inject,
+                      injection_schedule=schedule if inject else "all")
+            if ddim:
+                kw["eta"] = eta
+            loop = d.ddim_sample_loop_progressive if ddim else d.p_sample_loop_progressive
+            with SeqRandn(class_draw_order(T, inject=inject, schedule=schedule), 77, device=DEV) as rng:
+                runs[fused] = [(o["sample"].clone(), o["pred_xstart"].clone()) for o in loop(fn, (3, 3, 64, 64), **kw)]
+            assert rng.i == len(rng.seq)
+        assert len(runs["1"]) == T
+        for (s1, p1), (s0, p0) in zip(runs["1"], runs["0"]):
+            assert torch.equal(s1, s0) and torch.equal(p1, p0), (precision, ddim, schedule)
+        # the model is still usable through its ordinary call after a fused loop (the plan's inputs are re-packed)
+        x = torch.randn(3, 3, 64, 64, device=DEV)
+        t = torch.tensor([3, 7, 11], device=DEV)
+        a = fn(x, t, gt=gt, gt_keep_mask=keep)
+        b = fn(x, t, gt=gt, gt_keep_mask=keep)
+        assert torch.equal(a, b)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), s
     assert set(syms) == set(_lib.SYMBOLS), set(syms) ^ set(_lib.SYMBOLS)
-    assert _lib.lib().fidm_abi_version() == 2
+    assert _lib.lib().fidm_abi_version() == 3
 
 
 def test_ctypes_structs_match_header_field_order():
