@@ -49,7 +49,8 @@ struct ConvSwapParams {
   const float2* coef; int ld_coef;
   const float* bias;
   const float* row_add; int ld_row_add;
-  const unsigned short* residual; int ld_res;   // optional bf16 NHWC at output resolution
+  const unsigned short* residual; int ld_res;   // optional bf16 NHWC at output resolution ...
+  int res_half;                                 // ... or at HALF resolution (x_upd of an up ResBlock, nn.py:194): read (h/2, w/2)
   unsigned short* y; int ld_y;                  // bf16 NHWC output (a channel slice of a wider buffer when ld_y > cout)
   float* colsum; int colsum_slots; int cout;
   float* y_nchw; int cout_valid;
@@ -410,6 +411,8 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
       float s1a = 0.0f, s1b = 0.0f, s2a = 0.0f, s2b = 0.0f;
       const long long pix0 = ((long long)n * p.H + h0) * p.W + w0;          // first pixel of this warpgroup's first row
       const unsigned short* rp = p.residual ? p.residual + pix0 * p.ld_res + c : nullptr;
+      if (p.residual && p.res_half)      // first source pixel of this warpgroup's first row (h0, w0 are even)
+        rp = p.residual + (((long long)n * (p.H >> 1) + (h0 >> 1)) * (p.W >> 1) + (w0 >> 1)) * p.ld_res + c;
       unsigned short* yp = kHead ? nullptr : p.y + pix0 * p.ld_y + c;
 
       PF_T0();
@@ -422,9 +425,15 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         PF_T0();
         unsigned short rv[16];
         if (!kHead && rp) {                    // issued before the accumulator read: the loads fly under tcgen05.ld
-          const unsigned short* r0 = rp + (long long)chunk * p.W * p.ld_res;
+          if (p.res_half) {                    // nearest-2x upsampled residual: source pixel (row >> 1, col >> 1)
+            const unsigned short* r0 = rp + (long long)(chunk >> 1) * (p.W >> 1) * p.ld_res;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) rv[q] = __ldg(r0 + (long long)q * p.ld_res);
+            for (int q = 0; q < 16; q += 2) rv[q] = rv[q + 1] = __ldg(r0 + (long long)(q >> 1) * p.ld_res);
+          } else {
+            const unsigned short* r0 = rp + (long long)chunk * p.W * p.ld_res;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) rv[q] = __ldg(r0 + (long long)q * p.ld_res);
+          }
         }
         PF_ADD(pf_buf);
         PF_T0();
@@ -493,7 +502,7 @@ bool conv_halo_swap_supported(const fidm_conv_args& a) {
   using namespace halo_s;
   if (!(a.ksize == 3 && a.stride == 1 && a.height % kT == 0 && a.width % kT == 0 && a.cin % 64 == 0 && a.cin > 0 &&
         a.cin <= kMaxCin)) return false;
-  if (a.x_half_res || a.residual_half_res) return false;
+  if (a.x_half_res) return false;          // the up-sampling transform stays with K1h
   if (!(a.dtype == FIDM_F16 || a.dtype == FIDM_BF16)) return false;
   if (a.y_nchw_f32) return a.cout == 16 && !a.x2 && !a.residual && !a.colsum;
   return a.cout % 128 == 0;
@@ -517,6 +526,7 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, uns
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = kHead ? nullptr : reinterpret_cast<const unsigned short*>(a.residual); p.ld_res = a.ld_res;
+  p.res_half = a.residual_half_res;
   p.y = reinterpret_cast<unsigned short*>(a.y); p.ld_y = a.ld_y;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = p.tiles_w * p.tiles_h * 4;            // == fidm_conv_colsum_slots(H, W): one slot per 64 pixels
@@ -547,7 +557,7 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, uns
 int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof) {
   FIDM_REQUIRE(conv_halo_swap_supported(a), FIDM_E_SHAPE,
                "conv (fused GroupNorm operand, swapped roles): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, "
-               "cout %% 128 == 0 (or the 16-wide fp32-NCHW head), full-resolution input and residual");
+               "cout %% 128 == 0 (or the 16-wide fp32-NCHW head), full-resolution input");
   const bool f16 = a.dtype == FIDM_F16;
   if (prof && f16 && !a.y_nchw_f32) return launch_conv_halo_swap_t<true, false, true>(a, st, prof);   // instrumented (probe only)
   if (a.y_nchw_f32) return f16 ? launch_conv_halo_swap_t<true, true>(a, st) : launch_conv_halo_swap_t<false, true>(a, st);
