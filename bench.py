@@ -203,7 +203,8 @@ def main():
                     help="ddpm: p_sample_loop over all --ddim-steps timesteps (BASELINE configs[2]: DDPM-1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-only", action="store_true", help="only time UNet evaluations (ms per eval)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp8"],
+                    help="fp8: opt-in mode, the large GroupNorm-fused 3x3 convs on e4m3 operands (not the headline precision)")
     ap.add_argument("--preset", default=None, choices=sorted(PRESETS))
     ap.add_argument("--global-batch", type=int, default=None,
                     help="strong scaling: this many images split over the ranks (per-GPU batch = G / N)")
@@ -359,7 +360,10 @@ def main():
         "vs_baseline": None, "dtype": args.precision,
         "dtype_note": ("bf16 residual stream / qkv / attention operands; NORMALIZED conv operands (GroupNorm outputs) and the "
                        "weights they multiply are fp16 -- same width and tensor rate as bf16, 11-bit mantissa, saturating "
-                       "converts; fp32 accumulation") if args.precision == "bf16" else "FFMA verification mode",
+                       "converts; fp32 accumulation") if args.precision == "bf16" else
+                      ("OPT-IN reduced precision: as bf16, but the large GroupNorm-fused 3x3 convolutions multiply e4m3 "
+                       "operands with e4m3 weights (per-output-channel scale); outside the north star's eps bar"
+                       if args.precision == "fp8" else "FFMA verification mode"),
         "data": "synthetic",
         "config": {"workload": wl["label"], "preset": args.preset, "per_gpu_batch": B, "global_batch": B * world, "ddim_steps": T,
                    "parallelism": f"batch-sharded x{world}, no collective in the loop, one all_gather of the outputs",
@@ -378,6 +382,9 @@ def main():
                                         "weights fp16; fp32 accumulation, statistics, softmax and sampler state")
     if rank == 0:
         line["roofline"] = dominant_kernel_roofline(ops, dev, pk, B)
+        if args.precision == "fp8":
+            line["roofline_fp8"] = fp8_kernel_roofline(ops, dev, B)
+            line["config"]["fp8_convs_per_eval"] = plan.n_fp8
         line["hbm_kernels"] = hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S)
         if world == 1 and not args.no_cpu_baseline:
             evals = 2 if S == 256 else 5
@@ -499,6 +506,50 @@ def hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S):
                                      "achieved_gbs": by_k4b / ms_k4b / 1e6,
                                      "frac_of_hbm_peak": by_k4b / ms_k4b / 1e6 / pk["hbm_gbs"]},
             "peak_gbs": pk["hbm_gbs"], "peak_src": pk["src"]}
+
+
+def measured_fp8_peak(dev):
+    """Dense e4m3 GEMM throughput of this GPU, measured here (torch._scaled_mm -> cuBLASLt, 8192^3, best of 10):
+    the denominator of the FP8 kernel's roofline -- the bf16 peak of MEASURED_PEAKS.json is not reused."""
+    n = 8192
+    a = torch.randn(n, n, device=dev).to(torch.float8_e4m3fn)
+    b = torch.randn(n, n, device=dev).to(torch.float8_e4m3fn).t()          # column-major B, as cuBLASLt wants
+    one = torch.ones((), device=dev)
+    best = 1e9
+    for i in range(13):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def fp8_kernel_roofline(ops, dev, B):
+    """The dominant layer (conv 3x3 256->256 @256x256) on the opt-in e4m3 path, timed alone, against the FP8 GEMM
+    throughput measured in this run."""
+    import math
+    Cin = Cout = 256
+    H = W = 256
+    x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+    w8, scale = ops.quantize_weight_e4m3(ops.repack_weight(torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9),
+                                                              torch.float32))
+    b = torch.zeros(Cout, device=dev)
+    y = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    coef = ops.groupnorm_silu_coeff(x, torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev))
+    ms = _time_launches(lambda: ops.conv2d(x, w8, b, out=y, impl="tc", gn_coef=coef, w_scale=scale))
+    flops = 2.0 * B * H * W * Cout * Cin * 9
+    ach = flops / (ms * 1e-3) / 1e12
+    try:
+        peak = measured_fp8_peak(dev)
+        src = "torch._scaled_mm e4m3 8192^3, best of 10, measured in this run"
+    except Exception as e:          # pragma: no cover
+        peak, src = 4500.0, f"nominal dense fp8 (measurement failed: {e})"
+    return {"kernel": "conv_halo_kernel<256, e4m3> (GroupNorm+SiLU operand path + 3x3 conv, 256->256, 256x256, batch %d)" % B,
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_src": src,
+            "ms_per_launch": ms, "flops_per_launch": flops}
 
 
 def dominant_kernel_roofline(ops, dev, pk, B):

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FIDM_LIB_PATH: A/B experiments against an older build of the library (symbols it lacks are skipped)
 LIB_PATH = os.environ.get("FIDM_LIB_PATH") or os.path.join(_HERE, "libfidm_b200.so")
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, E4M3 = 0, 1, 2, 3
 COEF_COLS = 20
 STEP_INJECT_ONLY, STEP_UPDATE_ONLY, STEP_UPDATE_INJECT = 0, 1, 2
 SAMPLER_DDPM, SAMPLER_DDIM, SAMPLER_DDIM_SCRIPT = 0, 1, 2
@@ -58,7 +58,8 @@ class ConvArgs(C.Structure):
                 ("residual", vp), ("ld_res", i32), ("y", vp), ("ld_y", i32),
                 ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp),
                 ("splitk_ws", vp), ("splitk_ws_bytes", C.c_int64),
-                ("gn_coef", fp), ("ld_gn_coef", i32), ("x_half_res", i32), ("residual_half_res", i32)]
+                ("gn_coef", fp), ("ld_gn_coef", i32), ("x_half_res", i32), ("residual_half_res", i32),
+                ("w_scale", fp)]
 
 
 class AttnArgs(C.Structure):
@@ -146,6 +147,8 @@ def dtype_code(dt):
         return F32
     if dt == torch.float16:
         return F16
+    if dt in (torch.float8_e4m3fn, torch.uint8):
+        return E4M3
     raise ValueError(f"unsupported dtype {dt}")
 
 

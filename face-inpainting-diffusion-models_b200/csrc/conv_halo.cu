@@ -45,6 +45,7 @@ struct ConvHaloParams {
   int kc1, cin1;            // Cin / 64, Cin
   int kc2;                  // Cin2 / 64 of the optional 1x1 second source
   const float2* coef; int ld_coef;   // [B][ld_coef] (A/2, B/2) per (image, input channel)
+  const float* w_scale;     // optional per-output-channel scale of the accumulator (e4m3 weights)
   const float* bias;
   const float* row_add; int ld_row_add;
   const __nv_bfloat16* residual; int ld_res;
@@ -111,13 +112,37 @@ __device__ __forceinline__ uint32_t act_pair(uint32_t raw, float a0, float b0, f
   return *reinterpret_cast<const uint32_t*>(&o);
 }
 
-template <int BLOCK_N, bool OUT_F16, bool UP, bool PROF>
+// FP8 operand (tcgen05 kind::f8f6f4, e4m3): silu(x*A + B) of two packed bf16 values -> two packed e4m3 bytes (channel 0 in
+// the low byte).  satfinite: e4m3 has no inf, values beyond 448 clamp.
+__device__ __forceinline__ uint32_t act_pair_e4m3(uint32_t raw, float a0, float b0, float a1, float b1) {
+  const float h0 = fmaf(__uint_as_float(raw << 16), a0, b0);
+  const float h1 = fmaf(__uint_as_float(raw & 0xFFFF0000u), a1, b1);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  const float y0 = fmaf(h0, t0, h0), y1 = fmaf(h1, t1, h1);
+  unsigned short o;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(o) : "f"(y1), "f"(y0));
+  return (uint32_t)o;
+}
+__device__ __forceinline__ void st_shared_u32x2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+// OPK: operand kind staged by the transform and multiplied with the weights: 0 = bf16, 1 = fp16 (kind::f16),
+// 2 = fp8 e4m3 (kind::f8f6f4: a 128-byte operand row holds 128 channels, so a K slice is TWO 64-channel halo tiles;
+// BLOCK_N = 256, no UP).
+template <int BLOCK_N, int OPK, bool UP, bool PROF>
 __global__ void __launch_bounds__(halo::kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
                  const ConvHaloParams p) {
   using namespace halo;
+  constexpr bool OUT_F16 = OPK == 1;
+  constexpr bool FP8 = OPK == 2;
+  static_assert(!FP8 || (BLOCK_N == 256 && !UP), "fp8 operands: 256-wide tiles, no upsampling transform");
+  constexpr int kKW = FP8 ? 128 : 64;                    // channels per K slice (= per 128-byte operand row)
   constexpr int kBBytes = (BLOCK_N / 2) * 128;           // this CTA's half of one weight tile
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static_assert(BLOCK_N == 16 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -194,11 +219,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
         const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * kTH;
         const int n0 = m_blk / tiles_img;
         const int co0 = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
-        for (int kc = 0; kc < p.kc1; ++kc)
+        for (int kc = 0; kc < p.cin1 / kKW; ++kc)
           for (int s = 0; s < 3; ++s)
             for (int r = 0; r < 3; ++r) {
               acquire(kBBytes);
-              tma_load_2d_2sm(&tmB, &ring_full[stage], ring + stage * kRingStageBytes, (r * 3 + s) * p.cin1 + kc * 64, co0);
+              tma_load_2d_2sm(&tmB, &ring_full[stage], ring + stage * kRingStageBytes, (r * 3 + s) * p.cin1 + kc * kKW, co0);
               advance();
             }
         for (int kc = 0; kc < p.kc2; ++kc) {
@@ -230,7 +255,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
     } else if (warp == 14 && lane == 0 && cta_rank == 0) {
       // ================================================================ MMA issuer (leader CTA)
       constexpr uint32_t idesc_bf16 = umma_idesc_bf16(256, BLOCK_N);
-      constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(256, BLOCK_N) : idesc_bf16;
+      // kind::f8f6f4 with e4m3 x e4m3 -> f32 has the same descriptor bits as kind::f16 with f16 x f16 (format code 0)
+      constexpr uint32_t idesc_main = (OUT_F16 || FP8) ? umma_idesc_f16(256, BLOCK_N) : idesc_bf16;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t g = 0;
@@ -244,7 +270,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         uint32_t accum = 0;
-        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+        for (int kc = 0; kc < p.cin1 / kKW; ++kc, ++g) {
           for (int s = 0; s < 3; ++s) {
             if constexpr (PROF) pf_t = clock64();
             mbar_wait(&a_full[s], g & 1u);
@@ -258,8 +284,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
               const uint64_t da = umma_desc_sw128(copy_addr + s * kCopyBytes + r * 1024);
               const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_main, accum);
+              for (int k = 0; k < 4; ++k) {      // 4 x 32 bytes of K inside the 128-byte swizzle atom (16 x 16-bit | 32 x fp8)
+                if constexpr (FP8) umma_f8_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_main, accum);
+                else umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_main, accum);
                 accum = 1;
               }
               umma_commit_2sm(&ring_empty[stage], 3);
@@ -408,6 +435,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
         in_copy[s] = (unsigned)xx < 8u;
         so[s] = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + ((j ^ (xx & 7)) << 4);
       }
+      // fp8: the thread's 8 channels are 8 bytes: 16-byte chunk (4 half + j / 2) of the row, upper or lower half of it
+      uint32_t so8a[3], so8b[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x - s;
+        const uint32_t row = copy_addr + s * kCopyBytes + (yh * 8 + (xx & 7)) * 128 + (j & 1) * 8;
+        so8a[s] = row + (((j >> 1) ^ (xx & 7)) << 4);
+        so8b[s] = row + (((4 + (j >> 1)) ^ (xx & 7)) << 4);
+      }
       for (int wu = unit; wu < total_units; wu += n_units) {
         const int m_blk = (wu / p.n_blocks) * 2 + (int)cta_rank;
         const int w0 = (m_blk % p.tiles_w) * kTW;
@@ -429,6 +465,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
           if constexpr (PROF) pf_raw += clock64() - pf_t;
           if constexpr (PROF) pf_t = clock64();
           const uint32_t roff = rb * kRawStride;
+          if constexpr (FP8) {
+            // Two 64-channel halo tiles make one K slice: tile `half` fills bytes [64 half, 64 half + 64) of every
+            // 128-byte operand row (8 channels of a thread = 8 bytes); the copies are published after the second tile.
+            const uint32_t half = (uint32_t)kc & 1u, G = g >> 1;
+            uint2 v8[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+              uint32_t r1, r2, r3;
+              const uint32_t r0 = ld_shared_u32x4(((i & 1) ? ro_odd : ro_even) + roff + (i >> 1) * (4 * kHW * 128), r1, r2, r3);
+              v8[i].x = act_pair_e4m3(r0, c[0].x, c[0].y, c[0].z, c[0].w) | (act_pair_e4m3(r1, c[1].x, c[1].y, c[1].z, c[1].w) << 16);
+              v8[i].y = act_pair_e4m3(r2, c[2].x, c[2].y, c[2].z, c[2].w) | (act_pair_e4m3(r3, c[3].x, c[3].y, c[3].z, c[3].w) << 16);
+              const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+              if (out) v8[i] = make_uint2(0u, 0u);
+            }
+            if constexpr (PROF) pf_work += clock64() - pf_t;
+            if (half == 0) {                         // first tile: nothing is published, but the raw buffer is free again
+              named_bar_sync(7, 160);
+              if (tt == 0) mbar_arrive(&raw_empty[rb]);
+            }
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              if (half == 0) {
+                if constexpr (PROF) pf_t = clock64();
+                mbar_wait(&a_empty[s], (G & 1u) ^ 1u);
+                if constexpr (PROF) pf_ae += clock64() - pf_t;
+              }
+              if (in_copy[s]) {
+                const uint32_t base = (half ? so8b[s] : so8a[s]);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) st_shared_u32x2(base + i * 2048, v8[i].x, v8[i].y);
+              }
+              if (half == 1) {
+                fence_proxy_async_smem();
+                named_bar_sync(7, 160);
+                if (tt == 0) {
+                  if (s == 0) mbar_arrive(&raw_empty[rb]);
+                  mbar_arrive_cluster(&a_full[s], 0);
+                }
+              }
+            }
+          } else {
           uint4 v[9];
 #pragma unroll
           for (int i = 0; i < 9; ++i) {
@@ -458,6 +535,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
               mbar_arrive_cluster(&a_full[s], 0);
             }
           }
+          }  // 16-bit operands
         }
       }
     }
@@ -541,6 +619,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
           }
 #pragma unroll
           for (int q = 0; q < 32; ++q) { f[q] = __uint_as_float(v0[q]); f[32 + q] = __uint_as_float(v1[q]); }
+        }
+        if (p.w_scale) {      // dequantisation of e4m3 weights: per-output-channel scale on the accumulator, before the bias
+          const float4* s4 = reinterpret_cast<const float4*>(p.w_scale + cbase);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 t = __ldg(s4 + q);
+            f[4 * q] *= t.x; f[4 * q + 1] *= t.y; f[4 * q + 2] *= t.z; f[4 * q + 3] *= t.w;
+          }
         }
         if (p.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
@@ -654,10 +740,11 @@ bool conv_halo_supported(const fidm_conv_args& a) {
   return a.ksize == 3 && a.stride == 1 && a.height % halo::kTH == 0 && a.width % (2 * halo::kTW) == 0 &&
          a.cin % 64 == 0 && a.cin > 0 &&
          ((a.cout % 128 == 0 && !a.y_nchw_f32) || (a.cout == 16 && a.y_nchw_f32 && !a.x2 && !a.residual && !a.colsum)) &&
-         (a.dtype == FIDM_F16 || a.dtype == FIDM_BF16);
+         (a.dtype == FIDM_F16 || a.dtype == FIDM_BF16 ||
+          (a.dtype == FIDM_E4M3 && a.cin % 128 == 0 && a.cout % 256 == 0 && !a.x_half_res && !a.y_nchw_f32 && a.w_scale));
 }
 
-template <int BLOCK_N, bool OUT_F16, bool UP, bool PROF = false>
+template <int BLOCK_N, int OPK, bool UP, bool PROF = false>
 static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   using namespace halo;
   ConvHaloParams p;
@@ -667,6 +754,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   p.kc1 = a.cin / 64; p.cin1 = a.cin;
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
   p.coef = reinterpret_cast<const float2*>(a.gn_coef); p.ld_coef = a.ld_gn_coef;
+  p.w_scale = OPK == 2 ? a.w_scale : nullptr;
   p.bias = a.bias; p.row_add = a.row_add; p.ld_row_add = a.ld_row_add;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.res_half = a.residual_half_res;
@@ -684,7 +772,11 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
   } else {
     if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHW, kHH, 1, 0))) return rc;
   }
-  if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, OUT_F16 ? 1 : 0))) return rc;
+  if (OPK == 2) {      // e4m3 weights: [cout][9 * cin] bytes, box = 128 channels x BLOCK_N / 2 rows
+    if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, 2))) return rc;
+  } else {
+    if ((rc = make_matrix_map(&tmB, a.w, 9 * a.cin, a.cout, 9 * a.cin, BLOCK_N / 2, OPK == 1 ? 1 : 0))) return rc;
+  }
   if (a.x2) {
     if ((rc = make_nhwc_map(&tmA2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kTW, kTH, 1, 0))) return rc;
     if ((rc = make_matrix_map(&tmB2, a.w2, a.cin2, a.cout, a.cin2, BLOCK_N / 2, 0))) return rc;
@@ -701,28 +793,29 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
     if ((rc = make_nhwc_map(&tmRes, a.residual, a.cout, a.width, a.height, a.batch, a.ld_res, kTW, kTH, 1, 0))) return rc;
   }
   static bool attr_set[kMaxDevices] = {};      // per (instantiation, device)
-  FIDM_CUDA(ensure_dynamic_smem(conv_halo_kernel<BLOCK_N, OUT_F16, UP, PROF>, kSmemBytes, attr_set));
+  FIDM_CUDA(ensure_dynamic_smem(conv_halo_kernel<BLOCK_N, OPK, UP, PROF>, kSmemBytes, attr_set));
   const int units = (p.tiles_w * p.tiles_h * p.B / 2) * p.n_blocks;
   const int slots = num_sms() / 2;
   const int grid = (units < slots ? units : slots) * 2;
-  FIDM_CUDA(launch_pdl(conv_halo_kernel<BLOCK_N, OUT_F16, UP, PROF>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmRaw, tmB, tmA2,
+  FIDM_CUDA(launch_pdl(conv_halo_kernel<BLOCK_N, OPK, UP, PROF>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmRaw, tmB, tmA2,
                        tmB2, tmY, tmRes, p));
   FIDM_CHECK_LAUNCH("conv_halo");
   return 0;
 }
 
 int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
-  if (conv_halo_swap_preferred(a)) {
+  if (a.dtype != FIDM_E4M3 && conv_halo_swap_preferred(a)) {
     FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                  "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
     return launch_conv_halo_swap(a, st, g_prof);
   }
   FIDM_REQUIRE(conv_halo_supported(a), FIDM_E_SHAPE,
                "conv (fused GroupNorm operand): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, cout %% 128 == 0 "
-               "(or the 16-wide fp32-NCHW head)");
+               "(or the 16-wide fp32-NCHW head); e4m3 operands: cin %% 128 == 0, cout %% 256 == 0, w_scale, no upsampling");
   FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");
   const bool f16 = a.dtype == FIDM_F16;
+  if (a.dtype == FIDM_E4M3) return launch_conv_halo_t<256, 2, false>(a, st);
   if (a.x_half_res) {
     FIDM_REQUIRE(a.cout != 16, FIDM_E_SHAPE, "conv (fused GroupNorm operand): the head variant does not upsample");
     if (a.cout % 256 == 0) return f16 ? launch_conv_halo_t<256, true, true>(a, st) : launch_conv_halo_t<256, false, true>(a, st);

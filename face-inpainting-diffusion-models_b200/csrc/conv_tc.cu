@@ -469,12 +469,15 @@ int make_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
 int make_matrix_map(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows, int f16) {
   EncodeTiledFn enc = get_encode_tiled();
   FIDM_REQUIRE(enc != nullptr, FIDM_E_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
-  FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 8 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
+  FIDM_REQUIRE(((uintptr_t)base % 16) == 0 && ld % 16 == 0, FIDM_E_ALIGN, "tensor map: base/stride must be 16-byte aligned");
+  // f16: 0 = bf16, 1 = fp16, 2 = 8-bit elements (e4m3 weights): a 128-byte box row is then 128 elements
+  const int esz = f16 == 2 ? 1 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, f16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FIDM_REQUIRE(r == CUDA_SUCCESS, FIDM_E_DRIVER, "cuTensorMapEncodeTiled(matrix cols=%d rows=%d ld=%d box=%d) failed: %d",
@@ -588,7 +591,8 @@ extern "C" int fidm_conv_gn_fusable(int32_t batch, int32_t height, int32_t width
 extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stream) {
   using namespace fidm;
   FIDM_REQUIRE(a && a->x && a->w && a->y, FIDM_E_BADARG, "conv_tc: null x/w/y");
-  FIDM_REQUIRE(a->dtype == FIDM_BF16 || a->dtype == FIDM_F16, FIDM_E_BADARG, "conv_tc: dtype must be bf16 or f16");
+  FIDM_REQUIRE(a->dtype == FIDM_BF16 || a->dtype == FIDM_F16 || (a->dtype == FIDM_E4M3 && a->gn_coef), FIDM_E_BADARG,
+               "conv_tc: dtype must be bf16 or f16 (e4m3 only with the fused GroupNorm operand path)");
   FIDM_REQUIRE((a->stride == 1 && (a->ksize == 1 || a->ksize == 3)) ||
                (a->stride == 2 && a->ksize == 3 && a->height % 2 == 0 && a->width % 2 == 0 && !a->gn_coef && !a->x2),
                FIDM_E_SHAPE, "conv_tc: stride 1 with ksize 1|3, or stride 2 with ksize 3 on an even-sized input");

@@ -204,6 +204,17 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with 8-bit float operands (kind::f8f6f4; e4m3 / e5m2 selected by the instruction descriptor): K = 32 per
+// instruction, i.e. the same 32 bytes of each operand row as kind::f16's K = 16.
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive::one on the mbarrier at this smem offset in every CTA of `mask` once the issued MMAs completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

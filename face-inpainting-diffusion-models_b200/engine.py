@@ -16,6 +16,11 @@ precision "bf16": tcgen05 tensor-core kernels, fp32 accumulate / statistics / so
                   qkv and attention tensors are bf16, the normalized conv operands (GroupNorm outputs) and
                   the weights they multiply are fp16 (same tensor rate, 8x smaller rounding error).
 precision "fp32": FFMA verification mode (north star: eps within rel-L2 1e-5 of the reference).
+precision "fp8":  opt-in: as "bf16", except that the large 3x3 convolutions behind a GroupNorm
+                  (cin % 128 == 0, cout % 256 == 0, >= FP8_MIN_PIXELS output pixels -- the 256->256 / 512->256 layers that
+                  hold over half of ADM256's FLOPs) multiply an e4m3 operand with e4m3 weights (per-output-channel scale)
+                  on tcgen05 kind::f8f6f4 at twice the bf16 rate.  Outside the north star's eps bar; reported with its own
+                  PSNR next to bf16.
 """
 import ctypes as C
 import math
@@ -85,6 +90,11 @@ class Weights:
 
     def __init__(self, topo: Topology, sd, device, precision):
         self.topo, self.device, self.precision = topo, device, precision
+        self.fp8 = precision == "fp8"
+        precision = "bf16" if self.fp8 else precision          # everything but the selected layers is the bf16 engine
+        self.tc = precision == "bf16"                           # tensor-core kernels (vs the FFMA verification mode)
+        self.conv8 = {}     # name -> (e4m3 krsc weight as uint8, fp32 per-output-channel scale)
+        self.skip8 = {}     # out_layers name -> bf16 1x1 skip weight pre-divided by that scale
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.code = L.dtype_code(self.dtype)
         self.conv = {}      # name -> (krsc weight, bias fp32, cin_pad, cout_pad, ksize)
@@ -93,7 +103,7 @@ class Weights:
         # and their range is bounded by the normalisation.  The unnormalized residual stream, the qkv /
         # attention tensors and everything they are multiplied with stay bf16.
         self.norm_dtype = torch.float16 if precision == "bf16" else torch.float32
-        if precision == "bf16" and os.environ.get("FIDM_NORM_DTYPE", "fp16") == "bf16":
+        if self.tc and os.environ.get("FIDM_NORM_DTYPE", "fp16") == "bf16":
             self.norm_dtype = torch.bfloat16          # A/B switch: pure-bf16 operands
         self.vec = {}       # name -> fp32 vector (GroupNorm gamma/beta)
         lib = L.lib()
@@ -108,7 +118,7 @@ class Weights:
             cout, cin, ks, _ = w.shape
             cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
             wdt = self.dtype
-            if normalized and precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, head):
+            if normalized and self.tc and tc_eligible(cin_pad, cout_pad, stride, head):
                 wdt = self.norm_dtype
             dst = torch.empty(cout_pad, ks, ks, cin_pad, device=device, dtype=wdt)
             L.check(lib.fidm_repack_weight_oihw_to_krsc(L.ptr(w), L.ptr(dst), L.dtype_code(wdt), cout, cin, ks,
@@ -118,6 +128,15 @@ class Weights:
             if extra_bias is not None:
                 b[:cout] += extra_bias
             self.conv[name] = (dst, b, cin_pad, cout_pad, ks)
+            if self.fp8 and normalized and ks == 3 and stride == 1 and cin_pad % 128 == 0 and cout_pad % 256 == 0:
+                # e4m3 copy: w = q * scale[c], scale[c] = max|w[c]| / 448 (the largest finite e4m3)
+                wk = torch.empty(cout_pad, ks, ks, cin_pad, device=device, dtype=torch.float32)
+                L.check(lib.fidm_repack_weight_oihw_to_krsc(L.ptr(w), L.ptr(wk), L.F32, cout, cin, ks, cout_pad, cin_pad,
+                                                            L.stream()), "repack fp8 " + name)
+                amax = wk.abs().amax(dim=(1, 2, 3)).clamp_min(1e-12)
+                scale = (amax / 448.0).contiguous()
+                q = (wk / scale[:, None, None, None]).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+                self.conv8[name] = (q.view(torch.uint8).contiguous(), scale)
 
         def norm(name):
             self.vec[name + ".weight"] = f32(name + ".weight")
@@ -143,6 +162,10 @@ class Weights:
                     # (the same predicate _conv applies); otherwise it is the SIMT kernel on bf16 operands
                     conv(n + ".out_layers.3", extra_bias=f32(n + ".skip_connection.bias"),
                          normalized=layer.skip != "conv1x1" or layer.cin % 64 == 0)
+                    if (n + ".out_layers.3") in self.conv8:
+                        # the 1x1 skip shares the accumulator that is later multiplied by the e4m3 scale: pre-divide it
+                        w2 = self.conv[n + ".skip_connection"][0].float() / self.conv8[n + ".out_layers.3"][1][:, None, None, None]
+                        self.skip8[n + ".out_layers.3"] = w2.to(torch.bfloat16).contiguous()
                 w = f32(n + ".emb_layers.1.weight")
                 emb_w.append(w)
                 emb_b.append(f32(n + ".emb_layers.1.bias"))
@@ -179,10 +202,11 @@ class Plan:
         topo = weights.topo
         dev, dt = weights.device, weights.dtype
         self.ops = []
+        self.n_fp8 = 0           # convolutions of this plan that run on the e4m3 path (precision "fp8")
         self.pool = _Pool(dev, dt)
         self.keep = []
         # fused GroupNorm statistics: per-storage [B, ld, 2] channel sums written by the producing convs
-        self.fuse_stats = os.environ.get("FIDM_FUSE_GN_STATS", "1") != "0" and weights.precision == "bf16"
+        self.fuse_stats = os.environ.get("FIDM_FUSE_GN_STATS", "1") != "0" and weights.tc
         # GroupNorm + SiLU applied in the consumer conv's operand path (K1h) where fidm_conv_gn_fusable() says so
         self.fuse_gn = os.environ.get("FIDM_FUSE_GN_APPLY", "1") != "0"
         self.fuse_up = os.environ.get("FIDM_FUSE_UPSAMPLE", "1") != "0"
@@ -325,7 +349,7 @@ class Plan:
 
     def _fusable(self, name, H, W):
         """True if conv `name` at HxW can apply its GroupNorm+SiLU input in the operand path (K1h)."""
-        if not (self.fuse_gn and self.w.precision == "bf16"):
+        if not (self.fuse_gn and self.w.tc):
             return False
         wt, _, cin_pad, cout_pad, ks = self.w.conv[name]
         return bool(self.lib.fidm_conv_gn_fusable(self.B, H, W, cin_pad, cout_pad, ks, 1))
@@ -383,8 +407,14 @@ class Plan:
         a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, Ho, Wo
         a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
         a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
+        use_fp8 = (gn_coef is not None and name in w.conv8 and not x_half and Ho * Wo >= self.FP8_MIN_PIXELS and
+                   (x2 is None or name in w.skip8))
+        if use_fp8:          # e4m3 operand x e4m3 weights (kind::f8f6f4), per-output-channel scale in the epilogue
+            w8, scale = w.conv8[name]
+            a.dtype, a.w, a.w_scale = L.E4M3, L.ptr(w8), L.ptr(scale)
+            self.n_fp8 += 1
         if x2 is not None:
-            w2 = w.conv[name2][0]
+            w2 = w.skip8[name] if use_fp8 else w.conv[name2][0]
             a.x2, a.ld_x2, a.cin2, a.w2 = x2.ptr, x2.ld, x2.channels, L.ptr(w2)
         a.bias = L.ptr(bias)
         if row_add is not None:
@@ -400,7 +430,7 @@ class Plan:
         a.cout_valid = cout_valid or cout_pad
         a.splitk_ws, a.splitk_ws_bytes = L.ptr(self.splitk_ws), self.splitk_ws.numel()
         self.keep.append(a)
-        tc_ok = (w.precision == "bf16" and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
+        tc_ok = (w.tc and tc_eligible(cin_pad, cout_pad, stride, nchw_out is not None) and
                  (x2 is None or x2.channels % 64 == 0) and (stride == 1 or (ks == 3 and Ho % 2 == 0 and Wo % 2 == 0)))
         assert tc_ok or (wt.dtype != torch.float16 and gn_coef is None)
         fn = self.lib.fidm_conv2d_nhwc_bf16 if tc_ok else self.lib.fidm_conv2d_nhwc_simt
@@ -439,13 +469,14 @@ class Plan:
         a.dtype, a.batch, a.tokens, a.heads, a.head_dim = w.code, self.B, qkv.H * qkv.W, heads, head_dim
         a.qkv, a.ld_qkv, a.out, a.ld_out = qkv.ptr, qkv.ld, out.ptr, out.ld
         self.keep.append(a)
-        tc_ok = (w.precision == "bf16" and head_dim == 64 and a.tokens % 64 == 0 and
+        tc_ok = (w.tc and head_dim == 64 and a.tokens % 64 == 0 and
                  hasattr(self.lib, "fidm_attention_qkv_nhwc_bf16") and Plan.TC_ATTENTION)
         fn = self.lib.fidm_attention_qkv_nhwc_bf16 if tc_ok else self.lib.fidm_attention_qkv_nhwc_simt
         self._op(fn, C.byref(a))
 
     TC_ATTENTION = True
     FUSE_MIN_PIXELS = int(os.environ.get("FIDM_FUSE_MIN_PIXELS", 128 * 128))
+    FP8_MIN_PIXELS = int(os.environ.get("FIDM_FP8_MIN_PIXELS", 128 * 128))
 
     # ------------------------------------------------------------------ layers
     def _block(self, blk, x, dst):

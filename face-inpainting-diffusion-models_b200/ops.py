@@ -62,6 +62,15 @@ def repack_weight(w, dtype=torch.bfloat16, cout_pad=None, cin_pad=None):
     return out
 
 
+def quantize_weight_e4m3(w_krsc_f32):
+    """KRSC fp32 weights -> (e4m3 bytes as uint8, per-output-channel fp32 scale): w ~= q * scale[c] with
+    scale[c] = max|w[c]| / 448, the largest finite e4m3 (precision "fp8", engine.Weights)."""
+    amax = w_krsc_f32.abs().amax(dim=(1, 2, 3)).clamp_min(1e-12)
+    scale = (amax / 448.0).contiguous()
+    q = (w_krsc_f32 / scale[:, None, None, None]).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8).contiguous(), scale
+
+
 def timestep_embedding(t, freqs, dim):
     out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
     L.check(L.lib().fidm_timestep_embedding(L.ptr(t.float().contiguous()), L.ptr(freqs), L.ptr(out), t.shape[0], dim,
@@ -129,10 +138,11 @@ def groupnorm_silu_coeff(x, gamma=None, beta=None, *, scale_shift=None, groups=3
 
 def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=None, w2=None, out=None,
            nchw_out_channels=None, impl="auto", want_chansum=False, gn_coef=None, x_half_res=False,
-           residual_half_res=False):
+           residual_half_res=False, w_scale=None):
     """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto".
     gn_coef [N, Cin, 2] (from groupnorm_silu_coeff): x is the raw bf16 stream and the conv operand is
-    silu(GroupNorm(x)), applied inside the kernel; w_krsc's dtype (fp16 | bf16) is the staged operand's dtype."""
+    silu(GroupNorm(x)), applied inside the kernel; w_krsc's dtype (fp16 | bf16 | e4m3 bytes) is the staged operand's
+    dtype.  w_scale [Cout] fp32: per-output-channel scale of e4m3 weights (see quantize_weight_e4m3)."""
     n, h, w, cin, ld = _nhwc(x)
     if x_half_res:            # x is the half-resolution source of an `up` ResBlock: the conv runs at 2h x 2w
         h, w = 2 * h, 2 * w
@@ -146,6 +156,9 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
         a.gn_coef, a.ld_gn_coef = L.ptr(gn_coef), gn_coef.stride(0) // 2
     a.cin, a.cout, a.ksize, a.stride = cin, cout, ks, stride
     a.x, a.ld_x, a.w = L.ptr(x), ld, L.ptr(w_krsc)
+    if w_scale is not None:
+        assert w_scale.dtype == torch.float32 and w_scale.numel() == cout
+        a.w_scale = L.ptr(w_scale)
     if x2 is not None:
         n2, h2, w2_, c2, ld2 = _nhwc(x2)
         assert (n2, h2, w2_) == (n, ho, wo)

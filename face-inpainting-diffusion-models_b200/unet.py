@@ -82,8 +82,9 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------ engine management
     def set_precision(self, precision):
-        """"bf16" (tcgen05 tensor cores) or "fp32" (FFMA verification mode)."""
-        if precision not in ("bf16", "fp32"):
+        """"bf16" (tcgen05 tensor cores), "fp32" (FFMA verification mode) or the opt-in "fp8" (bf16 engine with the large
+        GroupNorm-fused 3x3 convolutions on e4m3 operands, engine.py)."""
+        if precision not in ("bf16", "fp32", "fp8"):
             raise ValueError(precision)
         if precision != self.precision:
             self.precision = precision

@@ -30,6 +30,7 @@ extern "C" {
 #define FIDM_F32  0
 #define FIDM_BF16 1
 #define FIDM_F16  2   /* normalized conv operands (GroupNorm outputs) and their weights: 11-bit mantissa */
+#define FIDM_E4M3 3   /* opt-in FP8 mode: e4m3 weights (per-output-channel scale) x e4m3 normalized operand, fp32 accumulate */
 
 #define FIDM_E_BADARG   (-1)
 #define FIDM_E_SHAPE    (-2)   /* shape not supported by this kernel (caller picks another entry) */
@@ -253,6 +254,10 @@ typedef struct fidm_conv_args {
                                            height/width are the OUTPUT size */
   int32_t residual_half_res;            /* with gn_coef: residual is [batch][height/2][width/2] and is read at
                                            (h/2, w/2) -- x_upd of an `up` ResBlock (nn.py:194,212) */
+  const float* w_scale;                 /* dtype FIDM_E4M3 (tensor-core entry, with gn_coef, cin % 128 == 0, cout % 256 == 0):
+                                           w holds e4m3 bytes [cout][3][3][cin] and y = acc * w_scale[c] + bias[c] + ...;
+                                           the operand is staged as e4m3 (tcgen05 kind::f8f6f4, twice the bf16 rate);
+                                           w2 of the fused 1x1 skip stays bf16 and must be pre-divided by w_scale[c] */
 } fidm_conv_args;
 /* number of partial rows per image the tensor-core conv writes into `colsum` (0: not supported for this size) */
 int fidm_conv_colsum_slots(int32_t height, int32_t width);

@@ -233,3 +233,43 @@ def test_reduce_colsum_coeff_entry_matches_two_launches(cuda_lib):
     with pytest.raises(ValueError):
         L.check(cuda_lib.fidm_groupnorm_reduce_colsum_coeff(L.ptr(colsum), slots, L.ptr(chansum2), 768, 0, C.byref(a), L.ptr(coef),
                                                             768, L.stream()), "reduce_coeff")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,Cin2", [(1, 16, 16, 128, 256, 0), (2, 64, 64, 256, 256, 0), (2, 32, 48, 512, 256, 0),
+                                                 (2, 64, 64, 256, 512, 128), (8, 128, 128, 256, 256, 0)])
+def test_conv_halo_fp8_operands(cuda_lib, B, H, W, Cin, Cout, Cin2):
+    """Opt-in FP8 mode: the fused operand path with an e4m3 operand and e4m3 weights (per-output-channel
+    scale) on tcgen05 kind::f8f6f4.  Checked against torch fp32 on the SAME quantised operands (so the tolerance is the
+    accumulation's, not e4m3's) and, loosely, against the unquantised convolution."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda"
+    x, w, b, gamma, beta, g = _mk(B, H, W, Cin, Cout, seed=Cin + Cout + H)
+    wk = ops.repack_weight(w, torch.float32)
+    w8, scale = ops.quantize_weight_e4m3(wk)
+    coef = ops.groupnorm_silu_coeff(x, gamma, beta)
+    res = torch.randn(B, H, W, Cout, device=dev, generator=g).bfloat16()
+    kw = {}
+    if Cin2:
+        x2 = torch.randn(B, H, W, Cin2, device=dev, generator=g).bfloat16()
+        w2 = torch.randn(Cout, Cin2, 1, 1, device=dev, generator=g) / math.sqrt(Cin2)
+        w2s = (ops.repack_weight(w2, torch.float32) / scale[:, None, None, None]).bfloat16()      # pre-divided by the scale
+        kw = dict(x2=x2, w2=w2s)
+    y, cs = ops.conv2d(x, w8, b, residual=res, impl="tc", gn_coef=coef, w_scale=scale, want_chansum=True, **kw)
+    torch.cuda.synchronize()
+    act = _act(x, gamma, beta)
+    act_q = act.to(torch.float8_e4m3fn).float()
+    w_q = (w8.view(torch.float8_e4m3fn).float() * scale[:, None, None, None]).permute(0, 3, 1, 2).contiguous()   # KRSC -> OIHW
+    want_q = Fn.conv2d(act_q, w_q, b, padding=1) + res.float().permute(0, 3, 1, 2)
+    want = Fn.conv2d(act, w, b, padding=1) + res.float().permute(0, 3, 1, 2)
+    if Cin2:
+        skip = Fn.conv2d(x2.float().permute(0, 3, 1, 2), (w2s.float() * scale[:, None, None, None]).permute(0, 3, 1, 2))
+        want_q, want = want_q + skip, want + skip
+    got = y.float().permute(0, 3, 1, 2)
+    rq = ((got - want_q).norm() / want_q.norm()).item()
+    r = ((got - want).norm() / want.norm()).item()
+    # device tanh.approx + e4m3 rounding of values near a rounding boundary differ from torch's silu by an e4m3 ulp now and then
+    assert rq < 1.5e-2, rq
+    assert r < 6e-2, r
+    yf = y.float()
+    assert torch.allclose(cs[..., 0], yf.sum(dim=(1, 2)), rtol=1e-3, atol=0.5)
