@@ -275,8 +275,8 @@ def test_adm256_eval_batch8_matches_reference(cuda_lib, golden_dir, precision, t
     # a batch-1 plan of the same weights gives the same numbers for image 3 (tiles never mix images)
     one = m(x[3:4], gold["t"][3:4].to(DEV), masked_image=data["masked_image"][3:4], mask=data["mask"][3:4])
     # (the batch-1 plan picks other kernels -- split-K, two-pass GroupNorm below the fill threshold -- so in bf16 mode the
-    # two differ by their rounding points, each within the bar of the reference; fp32 mode is order-exact to 1e-6)
-    assert rel_l2(one.cpu(), out[3:4].cpu()) < (1e-2 if precision == "bf16" else 1e-6)
+    # two differ by their rounding points, each within the bar of the reference; fp32 mode differs by summation order only)
+    assert rel_l2(one.cpu(), out[3:4].cpu()) < (1e-2 if precision == "bf16" else 5e-6)
 
 
 def test_adm256_lora_merged_quadratic_matches_reference(cuda_lib, golden_dir):
