@@ -139,6 +139,61 @@ static int launch_attn_simt(const fidm_attn_args& a, cudaStream_t st) {
   return 0;
 }
 
+// Any other head dim (the reference takes heads = C / num_head_channels or num_heads, nn.py:245-249, so d can be 48, 96,
+// 192, 256 ... 1024): one warp per query row, online softmax over 32-key tiles, lane = key for the scores and
+// lane = channel (stride 32) for the output.  A correctness path for unusual constructor arguments, not a tuned kernel.
+constexpr int kGenericMaxD = 1024;
+template <typename T>
+__global__ void __launch_bounds__(128) attn_generic_kernel(const AttnSimtParams p) {
+  const fidm_attn_args& a = p.a;
+  extern __shared__ float sm[];
+  const int D = a.head_dim, C = a.heads * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q_s = sm + warp * D;                         // this warp's query row, pre-scaled
+  const int h = blockIdx.y, b = blockIdx.z;
+  const float s = 1.0f / sqrtf(sqrtf((float)D));
+  const T* base = reinterpret_cast<const T*>(a.qkv) + (long long)b * a.tokens * a.ld_qkv + h * D;
+  constexpr int kMaxO = kGenericMaxD / 32;
+  for (int q = blockIdx.x * 4 + warp; q < a.tokens; q += gridDim.x * 4) {
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) q_s[d] = to_f32<T>(base[(long long)q * a.ld_qkv + d]) * s;
+    __syncwarp();
+    float m = -INFINITY, l = 0.0f, o[kMaxO];
+#pragma unroll
+    for (int i = 0; i < kMaxO; ++i) o[i] = 0.0f;
+    for (int k0 = 0; k0 < a.tokens; k0 += 32) {
+      const int key = k0 + lane;
+      float sc = -INFINITY;
+      if (key < a.tokens) {
+        const T* kr = base + (long long)key * a.ld_qkv + C;
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(q_s[d], to_f32<T>(kr[d]) * s, acc);
+        sc = acc;
+      }
+      const float mn = fmaxf(m, warp_max(sc));
+      const float corr = expf(m - mn);
+      const float pv = expf(sc - mn);                 // 0 for keys past the end
+      l = l * corr + warp_sum(pv);
+      m = mn;
+#pragma unroll
+      for (int i = 0; i < kMaxO; ++i) o[i] *= corr;
+      const int nk = min(32, a.tokens - k0);
+      for (int kk = 0; kk < nk; ++kk) {
+        const float pk = __shfl_sync(0xffffffffu, pv, kk);
+        const T* vr = base + (long long)(k0 + kk) * a.ld_qkv + 2 * C;
+#pragma unroll
+        for (int i = 0; i < kMaxO; ++i)
+          if (i * 32 + lane < D) o[i] = fmaf(pk, to_f32<T>(vr[i * 32 + lane]), o[i]);
+      }
+    }
+    T* out = reinterpret_cast<T*>(a.out) + ((long long)b * a.tokens + q) * a.ld_out + h * D;
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int i = 0; i < kMaxO; ++i)
+      if (i * 32 + lane < D) out[i * 32 + lane] = from_f32<T>(o[i] * inv);
+  }
+}
+
 template <typename T>
 static int dispatch_attn_simt(const fidm_attn_args& a, cudaStream_t st) {
   switch (a.head_dim) {
@@ -148,7 +203,15 @@ static int dispatch_attn_simt(const fidm_attn_args& a, cudaStream_t st) {
     case 128: return launch_attn_simt<T, 128>(a, st);
     default: break;
   }
-  FIDM_REQUIRE(false, FIDM_E_SHAPE, "attention_simt: head_dim %d not in {16,32,64,128}", a.head_dim);
+  FIDM_REQUIRE(a.head_dim > 0 && a.head_dim <= kGenericMaxD, FIDM_E_SHAPE, "attention_simt: head_dim %d not in [1, %d]",
+               a.head_dim, kGenericMaxD);
+  AttnSimtParams p;
+  p.a = a;
+  const int qblocks = (a.tokens + 3) / 4;
+  dim3 grid(qblocks < 1024 ? qblocks : 1024, a.heads, a.batch);
+  attn_generic_kernel<T><<<grid, 128, 4 * a.head_dim * sizeof(float), st>>>(p);
+  FIDM_CHECK_LAUNCH("attention_generic");
+  return 0;
 }
 
 }  // namespace fidm

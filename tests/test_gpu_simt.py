@@ -64,7 +64,9 @@ def _attn_ref(qkv, heads):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,T,heads,d", [(2, 64, 4, 64), (1, 256, 4, 64), (2, 64, 4, 128), (1, 100, 2, 32),
-                                         (1, 1024, 2, 64)])
+                                         (1, 1024, 2, 64),
+                                         # head dims outside the tiled kernel's set (nn.py:245-249: d = C / heads is free):
+                                         (2, 64, 2, 96), (1, 100, 3, 48), (1, 256, 1, 256), (1, 64, 1, 1024), (2, 70, 2, 20)])
 def test_attention_simt(cuda_lib, dtype, B, T, heads, d):
     from fidm_b200 import ops
     torch.backends.cuda.matmul.allow_tf32 = False
