@@ -407,6 +407,7 @@ def test_fused_step_boundary_is_bit_identical(cuda_lib, monkeypatch, ddim, eta, 
             if ddim:
                 kw["eta"] = eta
             loop = d.ddim_sample_loop_progressive if ddim else d.p_sample_loop_progressive
+            d.clear_gt_noise_cache()          # the *_progressive generators do not clear it themselves (as in the reference)
             with SeqRandn(class_draw_order(T, inject=inject, schedule=schedule), 77, device=DEV) as rng:
                 runs[fused] = [(o["sample"].clone(), o["pred_xstart"].clone()) for o in loop(fn, (3, 3, 64, 64), **kw)]
             assert rng.i == len(rng.seq)
