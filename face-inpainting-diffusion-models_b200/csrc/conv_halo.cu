@@ -61,6 +61,7 @@ struct ConvHaloParams {
 namespace halo {
 constexpr int kThreads = 512;
 constexpr int kEpiWarps = 8;
+constexpr int kXfWarps = 5;                            // transform warps (8-12)
 constexpr int kTW = 8, kTH = 16;                       // output pixel box of one CTA
 constexpr int kHW = kTW + 2, kHH = kTH + 2;            // halo tile
 constexpr int kHaloPix = kHW * kHH;                    // 180
@@ -183,8 +184,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
   }
   if (warp == 14) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
-      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+      // the five transform warps never synchronise with each other: each arrives on the mbarriers itself
+      for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kXfWarps); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 2 * kXfWarps); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < kRingStages; ++i) { mbar_init(&ring_full[i], 2); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
       for (int i = 0; i < 2; ++i) mbar_init(&res_bar[i], 1);
@@ -409,9 +411,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
               }
             }
             fence_proxy_async_smem();
-            named_bar_sync(7, 160);
-            if (tt == 0) {
-              if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the source box
+            __syncwarp();
+            if (lane == 0) {
+              if (s == 0) mbar_arrive(&raw_empty[rb]);      // this warp has read its part of the source box
               mbar_arrive_cluster(&a_full[s], 0);
             }
           }
@@ -481,8 +483,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
             }
             if constexpr (PROF) pf_work += clock64() - pf_t;
             if (half == 0) {                         // first tile: nothing is published, but the raw buffer is free again
-              named_bar_sync(7, 160);
-              if (tt == 0) mbar_arrive(&raw_empty[rb]);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&raw_empty[rb]);
             }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
@@ -498,8 +500,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
               }
               if (half == 1) {
                 fence_proxy_async_smem();
-                named_bar_sync(7, 160);
-                if (tt == 0) {
+                __syncwarp();
+                if (lane == 0) {
                   if (s == 0) mbar_arrive(&raw_empty[rb]);
                   mbar_arrive_cluster(&a_full[s], 0);
                 }
@@ -529,9 +531,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
               for (int i = 0; i < 9; ++i) st_shared_u32x4(so[s] + i * 2048, v[i]);
             }
             fence_proxy_async_smem();
-            named_bar_sync(7, 160);
-            if (tt == 0) {
-              if (s == 0) mbar_arrive(&raw_empty[rb]);      // every transform thread has read the halo tile
+            __syncwarp();
+            if (lane == 0) {
+              if (s == 0) mbar_arrive(&raw_empty[rb]);      // this warp has read its part of the halo tile
               mbar_arrive_cluster(&a_full[s], 0);
             }
           }
