@@ -489,6 +489,22 @@ def hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S):
     ms_k4 = _time_launches(lambda: diffusion._step(L.STEP_UPDATE_INJECT, xs, t=T // 2, t_inject=T // 2 - 1, model_out=mo,
                                                    gt=gt, keep=keep, inject_noise=n, ddim=True, want_next=True), n=50)
     by_k4 = 64.0 * B * S * S
+    # the same launch without the Python launcher: 20 launches captured in a CUDA graph, replayed
+    ms_k4_graph = None
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            outs = [torch.empty_like(xs) for _ in range(2)]
+            with torch.cuda.graph(g, stream=side):
+                for i in range(20):
+                    diffusion._step(L.STEP_UPDATE_INJECT, xs, t=T // 2, t_inject=T // 2 - 1, model_out=mo, gt=gt, keep=keep,
+                                    inject_noise=n, ddim=True, want_next=True, next_buf=outs[i & 1])
+        torch.cuda.synchronize()
+        ms_k4_graph = _time_launches(g.replay, n=10) / 20
+    except Exception:          # pragma: no cover
+        pass
     # the same kernel on 64 images (268 MB per launch), where the launch latency no longer dominates
     B2 = 64
     xs2, mo2 = torch.randn(B2, 3, S, S, device=dev), torch.randn(B2, 6, S, S, device=dev)
@@ -501,7 +517,9 @@ def hbm_kernel_rooflines(ops, diffusion, dev, pk, B, S):
                                      "frac_of_hbm_peak": by_gn / ms_gn / 1e6 / pk["hbm_gbs"]},
             "sampler_step": {"bytes_per_launch": by_k4, "ms_per_launch": ms_k4, "achieved_gbs": by_k4 / ms_k4 / 1e6,
                              "frac_of_hbm_peak": by_k4 / ms_k4 / 1e6 / pk["hbm_gbs"],
-                             "note": "34 MB per launch at batch 8: launch-latency bound (includes the Python launcher)"},
+                             "note": "34 MB per launch at batch 8: launch-latency bound (includes the Python launcher)",
+                             "ms_per_launch_in_cuda_graph": ms_k4_graph,
+                             "frac_of_hbm_peak_in_cuda_graph": (by_k4 / ms_k4_graph / 1e6 / pk["hbm_gbs"]) if ms_k4_graph else None},
             "sampler_step_batch64": {"bytes_per_launch": by_k4b, "ms_per_launch": ms_k4b,
                                      "achieved_gbs": by_k4b / ms_k4b / 1e6,
                                      "frac_of_hbm_peak": by_k4b / ms_k4b / 1e6 / pk["hbm_gbs"]},

@@ -300,6 +300,9 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
       so[s] = copy_addr + s * kCopyBytes + (yh * 9) * 2048 + ((xx >> 3) & 1) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
     }
     const uint32_t coef_s = smem_u32(coef_tab) + (uint32_t)j * 64u;      // 8 channels x (A/2, B/2) per 16-byte chunk j
+    uint32_t coef_q[4];                                                  // rotated quarters, see the table fill below
+#pragma unroll
+    for (int q = 0; q < 4; ++q) coef_q[q] = (uint32_t)((q + (j >> 1)) & 3) * 16u;
     int coef_n = -1;
     uint32_t g = 0;
     long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t = 0;
@@ -315,8 +318,12 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         named_bar_sync(7, kXfThreads);
         const float4* src = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef);
         for (int i = tt; i < p.cin1 / 2; i += kXfThreads) {
+          // float4 i = channels 2i, 2i+1 = quarter (i & 3) of 16-byte chunk (i >> 2): the four quarters of a chunk are
+          // rotated by (chunk >> 1) so that the eight chunks of a warp's load fall into eight different bank groups
+          // (unrotated, chunks j and j + 2 collide: 4-way conflicts, a quarter of the kernel's shared wavefronts)
           const float4 t = __ldg(src + i);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(coef_tab) + (uint32_t)i * 16u), "f"(t.x), "f"(t.y),
+          const uint32_t ch = (uint32_t)i >> 2, off = ch * 64u + ((((uint32_t)i & 3u) + ((ch & 7u) >> 1)) & 3u) * 16u;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(coef_tab) + off), "f"(t.x), "f"(t.y),
                        "f"(t.z), "f"(t.w) : "memory");
         }
         named_bar_sync(7, kXfThreads);
@@ -335,7 +342,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
 #pragma unroll
         for (int q = 0; q < 4; ++q) {      // (A/2, B/2) of channels 2q, 2q+1 of this chunk, from the shared-memory table
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[q].x), "=f"(c[q].y), "=f"(c[q].z), "=f"(c[q].w)
-                       : "r"(coef_s + (uint32_t)(kc * 512 + q * 16)));
+                       : "r"(coef_s + (uint32_t)(kc * 512) + coef_q[q]));
         }
         uint4 v[9];
 #pragma unroll
