@@ -546,7 +546,11 @@ static int launch_gn(const fidm_gn_args& a, cudaStream_t st, float2* coef = null
     // workspace: [batch*groups*2] floats (mean, rstd) padded to doubles, then the per-block partials
     double* partials = a.stats + (long long)a.batch * a.groups;
     chunks = plan(hw);
-    const int cap = FIDM_GN_MAX_BLOCKS / a.batch > 0 ? FIDM_GN_MAX_BLOCKS / a.batch : 1;
+    int cap = FIDM_GN_MAX_BLOCKS / a.batch > 0 ? FIDM_GN_MAX_BLOCKS / a.batch : 1;
+    // At small batch `plan` cuts an image into ~1000 blocks of a few pixels each, and the last block's fixed-order fold
+    // over all of them IS the kernel (29 us for a 4 MB tensor at batch 1): keep at least 64 KB of the image per block.
+    const long long want = (long long)hw * a.channels * (long long)sizeof(T) / 65536;
+    if (want < cap) cap = want < 1 ? 1 : (int)want;
     if (chunks > cap) {
       p.pix_per_blk = (hw + cap - 1) / cap;
       chunks = (hw + p.pix_per_blk - 1) / p.pix_per_blk;
