@@ -106,7 +106,7 @@ class InpaintingModelFn:
         gt, keep = mk.get("gt"), mk.get("gt_keep_mask")
         masked_image, mask = mk.get("masked_image"), mk.get("mask")
         inner = self.model
-        if not hasattr(inner, "base_model") or not hasattr(inner.base_model, "plan_for") or len(shape) != 4:
+        if getattr(inner, "fused_plan", None) is None or len(shape) != 4:       # not this package's DiffusionInpaintingModel
             return None
         if masked_image is None or mask is None:
             if gt is None or keep is None:
