@@ -450,3 +450,39 @@ def test_fp8_mode_adm256_eval_and_loop(cuda_lib, golden_dir):
     print("adm256 ddim100 fp8", {k: round(v, 2) for k, v in r.items()})
     _record("adm256_ddim100_fp8", r)
     assert r["psnr_hole"] >= 25.0, r
+
+
+def test_factory_checkpoint_to_sample_on_gpu(cuda_lib, tmp_path):
+    """The reference's end-to-end call surface on the GPU (train_inpainting.py:199-262 + test_inp_ddim_100.py:373-385):
+    create_model_and_diffusion(checkpoint) with a `state_dict`-wrapped 3-channel base checkpoint, a fine-tuned 9-channel
+    state_dict loaded through the wrapper with strict=False, the model_fn closure and ddim_sample_loop -- against the
+    same weights evaluated by the CPU oracle."""
+    import fidm_b200 as F
+    from fidm_b200.train_inpainting import FFHQ_UNET_KWARGS
+    from fidm_b200.utils.synth import synth_batch, synth_state_dict
+    from oracle import unet_oracle as uor
+    base_cfg = dict(FFHQ_UNET_KWARGS, image_size=64, in_channels=3)
+    sd3 = synth_state_dict(base_cfg, seed=4, prefix="")
+    path = tmp_path / "base.pt"
+    torch.save({"state_dict": sd3}, path)
+    model, diffusion, info = F.create_model_and_diffusion(str(path), DEV, img_size=64)
+    assert info == {"missing_keys": [], "unexpected_keys": []}
+    assert diffusion.num_timesteps == 1000 and next(model.parameters()).is_cuda
+    cfg9 = dict(FFHQ_UNET_KWARGS, image_size=64, in_channels=9)
+    sd9 = synth_state_dict(cfg9, seed=6)                                   # "fine-tuned" weights, base_model.* keys
+    res = model.load_state_dict({"model_state_dict": sd9}["model_state_dict"], strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    data = synth_batch(2, 64, seed=3, device=DEV)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([900, 17], device=DEV)
+    fn = F.InpaintingModelFn(model)
+    out = fn(x, t, gt=data["gt"], gt_keep_mask=data["gt_keep_mask"])
+    with torch.no_grad():
+        want = uor.inpaint_forward(sd9, cfg9, x.cpu(), t.cpu(), data["masked_image"].cpu(), data["mask"].cpu())
+    assert rel_l2(out.cpu(), want) < 1e-2
+    # a short loop on a 10-step table through the public sampler call: the known region of every model input is exact
+    d10 = F.create_gaussian_diffusion(steps=10, learn_sigma=True, noise_schedule="quadratic")
+    torch.manual_seed(5)
+    s = d10.ddim_sample_loop(fn, (2, 3, 64, 64), model_kwargs={"gt": data["gt"], "gt_keep_mask": data["gt_keep_mask"]},
+                             device=DEV, use_inpainting_injection=True)
+    assert s.shape == (2, 3, 64, 64) and torch.isfinite(s).all()
