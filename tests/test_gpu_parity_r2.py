@@ -461,19 +461,19 @@ def test_factory_checkpoint_to_sample_on_gpu(cuda_lib, tmp_path):
     from fidm_b200.train_inpainting import FFHQ_UNET_KWARGS
     from fidm_b200.utils.synth import synth_batch, synth_state_dict
     from oracle import unet_oracle as uor
-    base_cfg = dict(FFHQ_UNET_KWARGS, image_size=64, in_channels=3)
+    base_cfg = dict(FFHQ_UNET_KWARGS, image_size=128, in_channels=3)
     sd3 = synth_state_dict(base_cfg, seed=4, prefix="")
     path = tmp_path / "base.pt"
     torch.save({"state_dict": sd3}, path)
-    model, diffusion, info = F.create_model_and_diffusion(str(path), DEV, img_size=64)
+    model, diffusion, info = F.create_model_and_diffusion(str(path), DEV, img_size=128)
     assert info == {"missing_keys": [], "unexpected_keys": []}
     assert diffusion.num_timesteps == 1000 and next(model.parameters()).is_cuda
-    cfg9 = dict(FFHQ_UNET_KWARGS, image_size=64, in_channels=9)
+    cfg9 = dict(FFHQ_UNET_KWARGS, image_size=128, in_channels=9)
     sd9 = synth_state_dict(cfg9, seed=6)                                   # "fine-tuned" weights, base_model.* keys
     res = model.load_state_dict({"model_state_dict": sd9}["model_state_dict"], strict=False)
     assert not res.missing_keys and not res.unexpected_keys
-    data = synth_batch(2, 64, seed=3, device=DEV)
-    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    data = synth_batch(2, 128, seed=3, device=DEV)
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(DEV)
     t = torch.tensor([900, 17], device=DEV)
     fn = F.InpaintingModelFn(model)
     out = fn(x, t, gt=data["gt"], gt_keep_mask=data["gt_keep_mask"])
@@ -483,6 +483,6 @@ def test_factory_checkpoint_to_sample_on_gpu(cuda_lib, tmp_path):
     # a short loop on a 10-step table through the public sampler call: the known region of every model input is exact
     d10 = F.create_gaussian_diffusion(steps=10, learn_sigma=True, noise_schedule="quadratic")
     torch.manual_seed(5)
-    s = d10.ddim_sample_loop(fn, (2, 3, 64, 64), model_kwargs={"gt": data["gt"], "gt_keep_mask": data["gt_keep_mask"]},
+    s = d10.ddim_sample_loop(fn, (2, 3, 128, 128), model_kwargs={"gt": data["gt"], "gt_keep_mask": data["gt_keep_mask"]},
                              device=DEV, use_inpainting_injection=True)
-    assert s.shape == (2, 3, 64, 64) and torch.isfinite(s).all()
+    assert s.shape == (2, 3, 128, 128) and torch.isfinite(s).all()
