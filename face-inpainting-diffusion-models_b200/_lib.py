@@ -59,7 +59,7 @@ class ConvArgs(C.Structure):
                 ("y_nchw_f32", i32), ("cout_valid", i32), ("colsum", fp),
                 ("splitk_ws", vp), ("splitk_ws_bytes", C.c_int64),
                 ("gn_coef", fp), ("ld_gn_coef", i32), ("x_half_res", i32), ("residual_half_res", i32),
-                ("w_scale", fp)]
+                ("halo_copy", i32), ("w_scale", fp)]
 
 
 class AttnArgs(C.Structure):

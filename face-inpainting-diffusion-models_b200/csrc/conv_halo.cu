@@ -806,6 +806,7 @@ static int launch_conv_halo_t(const fidm_conv_args& a, cudaStream_t st) {
 }
 
 int launch_conv_halo(const fidm_conv_args& a, cudaStream_t st) {
+  if (a.halo_copy) return launch_conv_halo_swap(a, st, nullptr);      // un-normalized operand through the halo path (stem)
   if (a.dtype != FIDM_E4M3 && conv_halo_swap_preferred(a)) {
     FIDM_REQUIRE(a.gn_coef && a.ld_gn_coef >= a.cin && (uintptr_t)a.gn_coef % 16 == 0 && a.ld_gn_coef % 2 == 0, FIDM_E_BADARG,
                  "conv (fused GroupNorm operand): gn_coef must be 16-byte aligned [batch][ld >= cin] float2");

@@ -25,8 +25,8 @@
 //     of the stored bf16 values) accumulate in registers.
 //   * Head (kHead): 16 weight rows are loaded (6 valid), fp32 NCHW stores straight from the accumulator -- a thread's
 //     16 pixels are one 64-byte row segment of its channel plane.
-//   * The optional 1x1 skip source (nn.py:184,212) rides the weight ring: per 64-channel slice its weights and two
-//     16 x 8 pixel boxes, consumed by two N = 128 instructions.
+//   * The optional 1x1 skip source (nn.py:184,212) rides the weight ring: per 64-channel slice two 16 x 8 pixel boxes in
+//     adjacent stages (one 256-row B operand) and its weights.
 //
 // Warp roles (640 threads, 96 registers): 0-7 epilogue (two warpgroups), 8-16 transform, 17 weight-ring producer,
 // 18 MMA issuer + TMEM owner, 19 halo producer.
@@ -80,6 +80,7 @@ constexpr int kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kOffCopy % 1024 == 0 && kOffRing % 1024 == 0, "swizzle-atom alignment");
 static_assert(kRawBytes <= kRawStride, "raw buffer");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kRingStages >= 4, "a skip-source slice needs up to 4 stages: alignment skip, two pixel boxes, weights");
 }  // namespace halo_s
 
 __device__ __forceinline__ uint32_t lds_u32x4(uint32_t addr, uint32_t& y, uint32_t& z, uint32_t& w) {
@@ -109,7 +110,9 @@ __device__ __forceinline__ uint32_t act_pair_s(uint32_t raw, float a0, float b0,
   return o;
 }
 
-template <bool OUT_F16, bool kHead, bool PROF>
+// ACT = false: the operand is x itself (16-bit, already in the weights' dtype) -- the stem convolution, which has no
+// GroupNorm in front of it (unet.py:55) but the same 3x3 structure; the transform is then a plain shifted copy.
+template <bool OUT_F16, bool kHead, bool PROF, bool ACT>
 __global__ void __launch_bounds__(halo_s::kThreads, 1)
 conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW2,
@@ -187,14 +190,21 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
               advance();
             }
         for (int kc = 0; kc < p.kc2; ++kc) {
-          acquire(kRingStageBytes);
-          tma_load_2d(&tmW2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
-          advance();
+          // the two 16 x 8 pixel boxes of the skip source must sit in ADJACENT stages (one N = 256 operand of 32 KB):
+          // a pair may not start in the last stage -- skip it (the consumer follows the same rule)
+          if (stage == kRingStages - 1) {
+            mbar_wait(&ring_empty[stage], phase ^ 1);
+            mbar_arrive(&ring_full[stage]);
+            advance();
+          }
           for (int hb = 0; hb < 2; ++hb) {
             acquire(kRingStageBytes);
             tma_load_4d(&tmX2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, w0, h0 + hb * 8, n0);
             advance();
           }
+          acquire(kRingStageBytes);
+          tma_load_2d(&tmW2, &ring_full[stage], ring + stage * kRingStageBytes, kc * 64, co0);
+          advance();
         }
       }
     } else if (warp == 19 && lane == 0) {
@@ -214,7 +224,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
     } else if (warp == 18 && lane == 0) {
       // ================================================================ MMA issuer
       constexpr uint32_t idesc_main = OUT_F16 ? umma_idesc_f16(128, 256) : umma_idesc_bf16(128, 256);
-      constexpr uint32_t idesc_skip = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_skip = umma_idesc_bf16(128, 256);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t g = 0;
@@ -253,21 +263,24 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
           }
         }
         for (int kc = 0; kc < p.kc2; ++kc) {
-          const int st_w = stage;
-          mbar_wait(&ring_full[stage], phase);
-          tc_fence_after();
-          if (++stage == kRingStages) { stage = 0; phase ^= 1; }
-          const uint64_t da = umma_desc_sw128(ring_addr + st_w * kRingStageBytes);
-          for (int hb = 0; hb < 2; ++hb) {
+          auto next = [&]() { if (++stage == kRingStages) { stage = 0; phase ^= 1; } };
+          if (stage == kRingStages - 1) {          // alignment skip, see the producer
             mbar_wait(&ring_full[stage], phase);
-            tc_fence_after();
-            const uint64_t db = umma_desc_sw128(ring_addr + stage * kRingStageBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem + (uint32_t)(hb * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_skip, 1u);
             umma_commit(&ring_empty[stage]);
-            if (++stage == kRingStages) { stage = 0; phase ^= 1; }
+            next();
           }
+          const int st_x = stage;                  // pixels: stages st_x, st_x + 1 (256 rows), then the weights
+          mbar_wait(&ring_full[stage], phase); next();
+          mbar_wait(&ring_full[stage], phase); next();
+          const int st_w = stage;
+          mbar_wait(&ring_full[stage], phase); next();
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(ring_addr + st_w * kRingStageBytes);
+          const uint64_t db = umma_desc_sw128(ring_addr + st_x * kRingStageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_skip, 1u);
+          umma_commit(&ring_empty[st_x]);
+          umma_commit(&ring_empty[st_x + 1]);
           umma_commit(&ring_empty[st_w]);
         }
         umma_commit(&tmem_full[acc]);
@@ -312,7 +325,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
       const int w0 = (tile % p.tiles_w) * kT;
       const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
       const int n0 = tile / tiles_img;
-      if (n0 != coef_n) {
+      if (ACT && n0 != coef_n) {
         // per-(image, channel) coefficients of this image -> shared memory (once per image: tiles of an image are
         // consecutive); the barriers keep warps that still read the old table apart from the copy
         named_bar_sync(7, kXfThreads);
@@ -339,10 +352,12 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         PF_ADD(pf_raw);
         PF_T0();
         float4 c[4];
+        if constexpr (ACT) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {      // (A/2, B/2) of channels 2q, 2q+1 of this chunk, from the shared-memory table
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[q].x), "=f"(c[q].y), "=f"(c[q].z), "=f"(c[q].w)
-                       : "r"(coef_s + (uint32_t)(kc * 512) + coef_q[q]));
+          for (int q = 0; q < 4; ++q) {    // (A/2, B/2) of channels 2q, 2q+1 of this chunk, from the shared-memory table
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[q].x), "=f"(c[q].y), "=f"(c[q].z), "=f"(c[q].w)
+                         : "r"(coef_s + (uint32_t)(kc * 512) + coef_q[q]));
+          }
         }
         uint4 v[9];
 #pragma unroll
@@ -350,12 +365,16 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
           const uint32_t sw = (uint32_t)((px0 + i * kHalo) & 7) << 4;
           uint32_t r1, r2, r3;
           const uint32_t r0 = lds_u32x4(raw0 + i * (kHalo * 128) + (j16 ^ sw), r1, r2, r3);
-          v[i].x = act_pair_s<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
-          v[i].y = act_pair_s<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
-          v[i].z = act_pair_s<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
-          v[i].w = act_pair_s<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
-          const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
-          if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if constexpr (ACT) {
+            v[i].x = act_pair_s<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+            v[i].y = act_pair_s<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+            v[i].z = act_pair_s<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+            v[i].w = act_pair_s<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+            const bool out = (i == 0) ? first_out : (i == 8) ? last_out : col_out;
+            if (out) v[i] = make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            v[i] = make_uint4(r0, r1, r2, r3);       // out-of-image pixels were zero-filled by the TMA load: that IS the padding
+          }
         }
         PF_ADD(pf_work);
         // The transform warps never synchronise with each other: every warp arrives on the mbarriers itself (count 9).
@@ -521,7 +540,7 @@ bool conv_halo_swap_preferred(const fidm_conv_args& a) {
   return on && conv_halo_swap_supported(a) && (a.y_nchw_f32 || a.cout % 256 != 0);
 }
 
-template <bool OUT_F16, bool kHead, bool PROF = false>
+template <bool OUT_F16, bool kHead, bool PROF = false, bool ACT = true>
 static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof = nullptr) {
   using namespace halo_s;
   ConvSwapParams p;
@@ -551,11 +570,11 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, uns
     tmX2 = tmW; tmW2 = tmW;
   }
   static bool attr_set[kMaxDevices] = {};
-  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead, PROF>, kSmemBytes, attr_set));
+  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT>, kSmemBytes, attr_set));
   const int units = p.tiles_w * p.tiles_h * p.B * p.n_blocks;
   const int sms = num_sms();
   const int grid = units < sms ? units : sms;
-  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead, PROF>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
+  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
                        tmW2, p));
   FIDM_CHECK_LAUNCH("conv_halo_swap");
   return 0;
@@ -566,6 +585,10 @@ int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned lon
                "conv (fused GroupNorm operand, swapped roles): needs 3x3 stride 1, H %% 16 == 0, W %% 16 == 0, cin %% 64 == 0, "
                "cout %% 128 == 0 (or the 16-wide fp32-NCHW head), full-resolution input");
   const bool f16 = a.dtype == FIDM_F16;
+  if (a.halo_copy) {        // no activation: x is the operand (stem)
+    FIDM_REQUIRE(!a.y_nchw_f32 && !a.gn_coef, FIDM_E_BADARG, "conv (halo copy): no head variant, no gn_coef");
+    return f16 ? launch_conv_halo_swap_t<true, false, false, false>(a, st) : launch_conv_halo_swap_t<false, false, false, false>(a, st);
+  }
   if (prof && f16 && !a.y_nchw_f32) return launch_conv_halo_swap_t<true, false, true>(a, st, prof);   // instrumented (probe only)
   if (a.y_nchw_f32) return f16 ? launch_conv_halo_swap_t<true, true>(a, st) : launch_conv_halo_swap_t<false, true>(a, st);
   return f16 ? launch_conv_halo_swap_t<true, false>(a, st) : launch_conv_halo_swap_t<false, false>(a, st);

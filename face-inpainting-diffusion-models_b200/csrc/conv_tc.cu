@@ -606,7 +606,7 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   if (a->residual)
     FIDM_REQUIRE((uintptr_t)a->residual % 16 == 0 && a->ld_res % 8 == 0, FIDM_E_ALIGN, "conv_tc: residual alignment");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->gn_coef) return launch_conv_halo(*a, st);      // GroupNorm + SiLU of the raw input applied in the operand path
+  if (a->gn_coef || a->halo_copy) return launch_conv_halo(*a, st);      // GroupNorm + SiLU of the raw input applied in the operand path
   if (a->cout % 64 != 0 || a->y_nchw_f32) {
     FIDM_REQUIRE(a->y_nchw_f32 && a->cout == 16 && !a->residual, FIDM_E_SHAPE,
                  "conv_tc: cout %d is only supported as the 16-wide fp32-NCHW head", a->cout);

@@ -390,7 +390,7 @@ class Plan:
         return coef
 
     def _conv(self, name, x, y, residual=None, row_add=None, x2=None, name2=None, stride=1, nchw_out=None,
-              cout_valid=None, stats=True, gn_coef=None, x_half=False, residual_half=False):
+              cout_valid=None, stats=True, gn_coef=None, x_half=False, residual_half=False, halo_copy=False):
         w = self.w
         wt, bias, cin_pad, cout_pad, ks = w.conv[name]
         assert x.channels == cin_pad, (name, x.channels, cin_pad)
@@ -407,6 +407,12 @@ class Plan:
         a.dtype, a.batch, a.height, a.width = L.dtype_code(wt.dtype), self.B, Ho, Wo
         a.cin, a.cout, a.ksize, a.stride = cin_pad, cout_pad, ks, stride
         a.x, a.ld_x, a.w = x.ptr, x.ld, L.ptr(wt)
+        # stem: one halo load per slice through the swapped-role kernel instead of one TMA box per tap, where the layer
+        # fills the machine (one 16 x 16 pixel box x 128 output channels per SM)
+        if (halo_copy and w.tc and ks == 3 and stride == 1 and Ho % 16 == 0 and Wo % 16 == 0 and cout_pad % 128 == 0 and
+                self.B * (Ho // 16) * (Wo // 16) * (cout_pad // 128) * 100 >= 148 * 75 and
+                os.environ.get("FIDM_STEM_HALO", "1") != "0"):
+            a.halo_copy = 1
         use_fp8 = (gn_coef is not None and name in w.conv8 and not x_half and Ho * Wo >= self.FP8_MIN_PIXELS and
                    (x2 is None or name in w.skip8))
         if use_fp8:          # e4m3 operand x e4m3 weights (kind::f8f6f4), per-output-channel scale in the epilogue
@@ -485,7 +491,7 @@ class Plan:
             last = k == len(layers) - 1
             if layer.kind == "stem":
                 y = dst
-                self._conv(layer.name, x, y)
+                self._conv(layer.name, x, y, halo_copy=True)
             elif layer.kind == "res":
                 y = self._res(layer, x, dst if last else None)
             elif layer.kind == "attn":

@@ -138,7 +138,7 @@ def groupnorm_silu_coeff(x, gamma=None, beta=None, *, scale_shift=None, groups=3
 
 def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=None, w2=None, out=None,
            nchw_out_channels=None, impl="auto", want_chansum=False, gn_coef=None, x_half_res=False,
-           residual_half_res=False, w_scale=None):
+           residual_half_res=False, w_scale=None, halo_copy=False):
     """x NHWC, w_krsc [Cout,k,k,Cin].  impl: "tc" (tcgen05), "simt", or "auto".
     gn_coef [N, Cin, 2] (from groupnorm_silu_coeff): x is the raw bf16 stream and the conv operand is
     silu(GroupNorm(x)), applied inside the kernel; w_krsc's dtype (fp16 | bf16 | e4m3 bytes) is the staged operand's
@@ -159,6 +159,7 @@ def conv2d(x, w_krsc, bias=None, *, stride=1, row_add=None, residual=None, x2=No
     if w_scale is not None:
         assert w_scale.dtype == torch.float32 and w_scale.numel() == cout
         a.w_scale = L.ptr(w_scale)
+    a.halo_copy = int(halo_copy)         # stem: x through the halo kernel without an activation
     if x2 is not None:
         n2, h2, w2_, c2, ld2 = _nhwc(x2)
         assert (n2, h2, w2_) == (n, ho, wo)

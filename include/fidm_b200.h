@@ -254,6 +254,10 @@ typedef struct fidm_conv_args {
                                            height/width are the OUTPUT size */
   int32_t residual_half_res;            /* with gn_coef: residual is [batch][height/2][width/2] and is read at
                                            (h/2, w/2) -- x_upd of an `up` ResBlock (nn.py:194,212) */
+  int32_t halo_copy;                    /* tensor-core entry, 3x3 stride 1, H % 16 == 0, W % 16 == 0, cin % 64 == 0, cout % 128 == 0,
+                                           no gn_coef: stage x (already in w's dtype) through the swapped-role halo kernel
+                                           (conv_halo_swap.cu) WITHOUT an activation: one halo load per 64-channel slice
+                                           instead of one box per tap -- the stem convolution (unet.py:55) */
   const float* w_scale;                 /* dtype FIDM_E4M3 (tensor-core entry, with gn_coef, cin % 128 == 0, cout % 256 == 0):
                                            w holds e4m3 bytes [cout][3][3][cin] and y = acc * w_scale[c] + bias[c] + ...;
                                            the operand is staged as e4m3 (tcgen05 kind::f8f6f4, twice the bf16 rate);

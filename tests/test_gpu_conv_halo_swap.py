@@ -100,3 +100,24 @@ def test_conv_swap_head(cuda_lib, B, H, W, Cin):
     assert y.shape == want.shape
     rel = ((y - want).norm() / want.norm()).item()
     assert rel < 3e-3, rel
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 16, 16, 64, 128), (2, 64, 48, 64, 256), (8, 256, 256, 64, 128)])
+def test_conv_swap_halo_copy_stem(cuda_lib, B, H, W, Cin, Cout):
+    """halo_copy: the stem convolution (unet.py:55: no GroupNorm in front) through the swapped-role kernel with the
+    transform reduced to a shifted copy -- plain conv3x3 of an fp16 input, bias, fused output statistics."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B + H + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).half()
+    x[..., 9:] = 0                                     # the packed 9-channel network input, zero-padded to 64
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * 9)).half()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y, cs = ops.conv2d(x, ops.repack_weight(w.float(), torch.float16), b, impl="tc", halo_copy=True, want_chansum=True)
+    y0 = ops.conv2d(x, ops.repack_weight(w.float(), torch.float16), b, impl="tc")
+    want = Fn.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)
+    _check(y, want, ("halo_copy", B, H, W, Cin, Cout))
+    _check(y0, want, ("K1", B, H, W, Cin, Cout))
+    yf = y.float()
+    assert torch.allclose(cs[..., 0], yf.sum(dim=(1, 2)), rtol=1e-3, atol=0.5)
+    assert torch.allclose(cs[..., 1], (yf * yf).sum(dim=(1, 2)), rtol=1e-3, atol=0.5)
