@@ -378,8 +378,9 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         }
         PF_ADD(pf_work);
         // The transform warps never synchronise with each other: every warp arrives on the mbarriers itself (count 9).
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[0]);        // this warp has read its part of the halo tile
+        // The halo buffer is released only after the first copy's stores: they depend on the loaded registers, so every
+        // ld.shared of this warp has completed by then (an arrive issued right behind the loads is NOT ordered after
+        // them -- with the activation compiled out (stem) the TMA refill overtook loads still in flight).
         // copy 0 is published on its own (the MMAs of this slice start with it); copies 1 and 2 share one proxy fence:
         // copy 1 is not needed before the three taps of copy 0 have been issued
 #pragma unroll
@@ -395,6 +396,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
+              if (s == 0) mbar_arrive(&raw_empty[0]);       // this warp has read its part of the halo tile
               if (s == 2) mbar_arrive(&a_full[1]);
               mbar_arrive(&a_full[s]);
             }
