@@ -25,17 +25,28 @@ struct AttnTcParams {
 };
 
 constexpr int kAttnThreads = 192;
-constexpr int BQ = 128, BK = 128, HD = 64;
-constexpr int kTileBytes = 128 * 128;     // 128 rows x 64 bf16, 128-byte swizzled
+constexpr int BQ = 128, BK = 128;
+constexpr int kSubBytes = 128 * 128;      // one sub-tile: 128 rows x 64 bf16, 128-byte swizzled
 constexpr int kKvStages = 2;
-// smem: Q | K[2] | V[2] | P (2 x 16 KB, reused as the output staging tile) | barriers.  112.25 KB: TWO CTAs per SM
-// (with 1 KB of system reserve each), so that one CTA's softmax overlaps the other's MMAs.  No alignment slack: the
-// dynamic shared window of a kernel without static shared memory starts 1024-byte aligned (checked at run time).
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kKvStages + 2) + 256;
-constexpr int kAttnTmemCols = 256;        // S: columns [0,128), O tile: [128,192)
+// HD = 64 | 128 (round 2: heads of 128 channels -- num_heads-defined heads, nn.py:245-249 -- on the tensor cores too).
+// A Q / K / V tile is HD / 64 sub-tiles of [128 rows][64 channels]; P is two sub-tiles of [128 queries][64 keys].
+// smem: Q | K[2] | V[2] | P (reused as the output staging tile) | barriers.  HD = 64: 112.25 KB, TWO CTAs per SM
+// (with 1 KB of system reserve each), so that one CTA's softmax overlaps the other's MMAs; HD = 128: 192.25 KB, one CTA.
+// No alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte aligned
+// (checked at run time).
+template <int HD> struct AttnCfg {
+  static constexpr int kSub = HD / 64;
+  static constexpr int kTileBytes = kSub * kSubBytes;
+  static constexpr int kSmem = kTileBytes * (1 + 2 * kKvStages) + 2 * kSubBytes + 256;
+  static constexpr int kCtasPerSm = HD == 64 ? 2 : 1;
+};
+constexpr int kAttnTmemCols = 256;        // S: columns [0,128), O tile: [128,128 + HD)
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<HD>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
+  constexpr int kSub = AttnCfg<HD>::kSub;
+  constexpr int kTileBytes = AttnCfg<HD>::kTileBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) {       // the 128-byte swizzle atoms need a 1024-byte aligned base
@@ -46,7 +57,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   uint8_t* sK = sQ + kTileBytes;
   uint8_t* sV = sK + kKvStages * kTileBytes;
   uint8_t* sP = sV + kKvStages * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kSubBytes);
   uint64_t* q_full = bars;               // 1
   uint64_t* kv_full = bars + 1;          // kKvStages
   uint64_t* kv_empty = kv_full + kKvStages;
@@ -86,13 +97,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   if (warp == 4) {
     if (lane == 0) {
       mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(&tmQKV, q_full, sQ, h * HD, q0, 0, b);
+#pragma unroll
+      for (int u = 0; u < kSub; ++u) tma_load_4d(&tmQKV, q_full, sQ + u * kSubBytes, h * HD + u * 64, q0, 0, b);
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
         mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
-        tma_load_4d(&tmQKV, &kv_full[stage], sK + stage * kTileBytes, p.C + h * HD, j * BK, 0, b);
-        tma_load_4d(&tmQKV, &kv_full[stage], sV + stage * kTileBytes, 2 * p.C + h * HD, j * BK, 0, b);
+#pragma unroll
+        for (int u = 0; u < kSub; ++u) {
+          tma_load_4d(&tmQKV, &kv_full[stage], sK + stage * kTileBytes + u * kSubBytes, p.C + h * HD + u * 64, j * BK, 0, b);
+          tma_load_4d(&tmQKV, &kv_full[stage], sV + stage * kTileBytes + u * kSubBytes, 2 * p.C + h * HD + u * 64, j * BK, 0, b);
+        }
         if (++stage == kKvStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -107,9 +122,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       {
-        const uint64_t dq = umma_desc_sw128(aQ), dk = umma_desc_sw128(smem_u32(sK));
+        const uint32_t aK = smem_u32(sK);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        for (int k = 0; k < HD / 16; ++k)       // 16 channels per instruction, 64 per sub-tile
+          umma_bf16(tmem_S, umma_desc_sw128(aQ + (k >> 2) * kSubBytes) + 2 * (k & 3),
+                    umma_desc_sw128(aK + (k >> 2) * kSubBytes) + 2 * (k & 3), idesc_s, k ? 1u : 0u);
         umma_commit(s_full);
       }
       for (int j = 0; j < n_kv; ++j) {
@@ -119,8 +136,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         const uint32_t aV = smem_u32(sV + stage * kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t dp = umma_desc_sw128(aP + (kk >> 2) * kTileBytes) + (uint64_t)(2 * (kk & 3));
-          const uint64_t dv = umma_desc_sw128_mn(aV + kk * 2048, 8192);
+          const uint64_t dp = umma_desc_sw128(aP + (kk >> 2) * kSubBytes) + (uint64_t)(2 * (kk & 3));
+          // V as the MN-major B operand: N = HD channels, 64 per sub-tile (LBO = distance between the 64-channel blocks)
+          const uint64_t dv = umma_desc_sw128_mn(aV + kk * 2048, kSubBytes);
           umma_bf16(tmem_O, dp, dv, idesc_o, kk ? 1u : 0u);
         }
         umma_commit(&kv_empty[stage]);
@@ -130,9 +148,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         if (j + 1 < n_kv) {
           mbar_wait(&kv_full[stage], phase);
           tc_fence_after();
-          const uint64_t dq = umma_desc_sw128(aQ), dk = umma_desc_sw128(smem_u32(sK + stage * kTileBytes));
+          const uint32_t aK = smem_u32(sK + stage * kTileBytes);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tmem_S, umma_desc_sw128(aQ + (k >> 2) * kSubBytes) + 2 * (k & 3),
+                      umma_desc_sw128(aK + (k >> 2) * kSubBytes) + 2 * (k & 3), idesc_s, k ? 1u : 0u);
           umma_commit(s_full);
         }
       }
@@ -179,7 +199,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           pv[i] = (c * 32 + i < kv_valid) ? e : 0.0f;
           rs += pv[i];
         }
-        uint8_t* chunk = prow + (c >> 1) * kTileBytes;     // 64 keys per swizzled K-chunk
+        uint8_t* chunk = prow + (c >> 1) * kSubBytes;      // 64 keys per swizzled K-chunk
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 pk;
@@ -217,7 +237,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     // ---- epilogue: O / l -> bf16 -> swizzled staging (reuses P chunk 0; the last PV MMA completed: o_full)
     const float inv = 1.0f / l_run;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < HD / 8; ++u) {       // 8 channels per 16-byte unit, 8 units per 64-channel sub-tile
       uint4 pk;
       __nv_bfloat162 b0 = __floats2bfloat162_rn(o[8 * u + 0] * inv, o[8 * u + 1] * inv);
       __nv_bfloat162 b1 = __floats2bfloat162_rn(o[8 * u + 2] * inv, o[8 * u + 3] * inv);
@@ -227,12 +247,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       pk.y = *reinterpret_cast<uint32_t*>(&b1);
       pk.z = *reinterpret_cast<uint32_t*>(&b2);
       pk.w = *reinterpret_cast<uint32_t*>(&b3);
-      *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pk;
+      *reinterpret_cast<uint4*>(prow + (u >> 3) * kSubBytes + (((u & 7) ^ (row & 7)) << 4)) = pk;
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (threadIdx.x == 0) {
-      tma_store_4d(&tmO, sP, h * HD, q0, 0, b);
+#pragma unroll
+      for (int u = 0; u < kSub; ++u) tma_store_4d(&tmO, sP + u * kSubBytes, h * HD + u * 64, q0, 0, b);
       bulk_commit_group();
       bulk_wait_group_read<0>();
     }
@@ -252,22 +273,28 @@ extern "C" int fidm_attention_qkv_nhwc_bf16(const fidm_attn_args* a, fidm_stream
   using namespace fidm;
   FIDM_REQUIRE(a && a->qkv && a->out, FIDM_E_BADARG, "attention_tc: null qkv/out");
   FIDM_REQUIRE(a->dtype == FIDM_BF16, FIDM_E_BADARG, "attention_tc: dtype must be bf16");
-  FIDM_REQUIRE(a->head_dim == 64, FIDM_E_SHAPE, "attention_tc: head_dim %d (only 64)", a->head_dim);
+  FIDM_REQUIRE(a->head_dim == 64 || a->head_dim == 128, FIDM_E_SHAPE, "attention_tc: head_dim %d (64 or 128)", a->head_dim);
   FIDM_REQUIRE(a->batch > 0 && a->tokens > 0 && a->heads > 0, FIDM_E_BADARG, "attention_tc: empty shape");
-  const int Cn = a->heads * 64;
+  const int Cn = a->heads * a->head_dim;
   FIDM_REQUIRE(a->ld_qkv >= 3 * Cn && a->ld_out >= Cn, FIDM_E_BADARG, "attention_tc: ld too small");
   AttnTcParams p;
   p.B = a->batch; p.T = a->tokens; p.heads = a->heads; p.C = Cn;
-  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.scale_log2 = (1.0f / sqrtf((float)a->head_dim)) * 1.4426950408889634f;     // (d^-1/4)^2 * log2(e)
   CUtensorMap tmQKV, tmO;
   int rc;
   // [B][T][3C] viewed as NHWC with H = 1: box = 64 channels x 128 tokens
   if ((rc = make_nhwc_map(&tmQKV, a->qkv, 3 * Cn, a->tokens, 1, a->batch, a->ld_qkv, 128, 1, 1, 0))) return rc;
   if ((rc = make_nhwc_map(&tmO, a->out, Cn, a->tokens, 1, a->batch, a->ld_out, 128, 1, 1, 0))) return rc;
-  static bool attr_set[kMaxDevices] = {};      // per (instantiation, device)
-  FIDM_CUDA(ensure_dynamic_smem(attn_tc_kernel, kAttnSmem, attr_set));
   dim3 grid((a->tokens + BQ - 1) / BQ, a->heads, a->batch);
-  FIDM_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(kAttnThreads), kAttnSmem, (cudaStream_t)stream, 1, tmQKV, tmO, p));
+  if (a->head_dim == 64) {
+    static bool attr_set[kMaxDevices] = {};      // per (instantiation, device)
+    FIDM_CUDA(ensure_dynamic_smem(attn_tc_kernel<64>, AttnCfg<64>::kSmem, attr_set));
+    FIDM_CUDA(launch_pdl(attn_tc_kernel<64>, grid, dim3(kAttnThreads), AttnCfg<64>::kSmem, (cudaStream_t)stream, 1, tmQKV, tmO, p));
+  } else {
+    static bool attr_set[kMaxDevices] = {};
+    FIDM_CUDA(ensure_dynamic_smem(attn_tc_kernel<128>, AttnCfg<128>::kSmem, attr_set));
+    FIDM_CUDA(launch_pdl(attn_tc_kernel<128>, grid, dim3(kAttnThreads), AttnCfg<128>::kSmem, (cudaStream_t)stream, 1, tmQKV, tmO, p));
+  }
   FIDM_CHECK_LAUNCH("attention_tc");
   return 0;
 }

@@ -475,7 +475,7 @@ class Plan:
         a.dtype, a.batch, a.tokens, a.heads, a.head_dim = w.code, self.B, qkv.H * qkv.W, heads, head_dim
         a.qkv, a.ld_qkv, a.out, a.ld_out = qkv.ptr, qkv.ld, out.ptr, out.ld
         self.keep.append(a)
-        tc_ok = (w.tc and head_dim == 64 and a.tokens % 64 == 0 and
+        tc_ok = (w.tc and head_dim in (64, 128) and a.tokens % 64 == 0 and
                  hasattr(self.lib, "fidm_attention_qkv_nhwc_bf16") and Plan.TC_ATTENTION)
         fn = self.lib.fidm_attention_qkv_nhwc_bf16 if tc_ok else self.lib.fidm_attention_qkv_nhwc_simt
         self._op(fn, C.byref(a))

@@ -215,7 +215,7 @@ def attention(qkv, heads, *, out=None, impl="auto"):
     a.dtype, a.batch, a.tokens, a.heads, a.head_dim = L.dtype_code(qkv.dtype), n, t, heads, d
     a.qkv, a.ld_qkv, a.out, a.ld_out = L.ptr(qkv), ld, L.ptr(y), y.stride(1)
     if impl == "auto":
-        impl = "tc" if (qkv.dtype == torch.bfloat16 and d == 64) else "simt"
+        impl = "tc" if (qkv.dtype == torch.bfloat16 and d in (64, 128) and t % 64 == 0) else "simt"
     fn = L.lib().fidm_attention_qkv_nhwc_bf16 if impl == "tc" else L.lib().fidm_attention_qkv_nhwc_simt
     L.check(fn(C.byref(a), L.stream()), "attention/" + impl)
     return y

@@ -281,7 +281,7 @@ int fidm_conv2d_nhwc_simt(const fidm_conv_args* a, fidm_stream_t stream);
  * K3  QKV attention over a [batch][tokens][3*C] NHWC qkv buffer (channel order
  * [Q heads | K heads | V heads], head-major inside each third, as nn.py:226-234 views it).
  * softmax_fp32((q*s)^T (k*s)) v with s = head_dim^-1/4, non-causal (nn.py:222-235).
- *   fidm_attention_qkv_nhwc_bf16 : tcgen05 flash-style kernel, head_dim 64, tokens % 64 == 0.
+ *   fidm_attention_qkv_nhwc_bf16 : tcgen05 flash-style kernel, head_dim 64 or 128, tokens % 64 == 0.
  *   fidm_attention_qkv_nhwc_simt : fp32 or bf16; tiled FFMA kernel for head_dim 16/32/64/128, a one-warp-per-query
  *                                  kernel for any other head_dim <= 1024 (nn.py:245-249 allows any C / heads).
  * ---------------------------------------------------------------------------------------------- */

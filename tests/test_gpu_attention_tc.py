@@ -18,12 +18,14 @@ def _attn_ref(qkv, heads):
     return a.permute(0, 2, 1)
 
 
+@pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("B,T,heads", [(1, 128, 1), (2, 64, 4), (1, 256, 8), (2, 1024, 8), (3, 192, 2)])
-def test_attention_tc(cuda_lib, B, T, heads):
+def test_attention_tc(cuda_lib, B, T, heads, d):
+    """head dims 64 and 128 (num_heads-defined heads of 512-channel blocks, nn.py:245-249) on the tcgen05 kernel"""
     from fidm_b200 import ops
     torch.backends.cuda.matmul.allow_tf32 = False
-    g = torch.Generator(device="cuda").manual_seed(T + heads)
-    buf = (torch.randn(B, T, 3 * heads * 64 + 64, device="cuda", generator=g) * 1.5).bfloat16()
+    g = torch.Generator(device="cuda").manual_seed(T + heads + d)
+    buf = (torch.randn(B, T, 3 * heads * d + 64, device="cuda", generator=g) * 1.5).bfloat16()
     qkv = buf[..., 64:]                                    # exercised through a strided view
     y = ops.attention(qkv, heads, impl="tc")
     torch.cuda.synchronize()
