@@ -66,6 +66,8 @@ constexpr int kEpiThreads = 128;                       // per epilogue warpgroup
 constexpr int kXfThreads = 288;                        // warps 8-16
 constexpr int kT = 16, kHalo = 18;
 constexpr int kRawBytes = kHalo * kHalo * 128;         // 41472: one halo tile of a 64-channel slice
+constexpr int kUp = 10;                                // source box of the halo under a nearest 2x upsample: 10 x 10
+constexpr int kRawBytesUp = kUp * kUp * 128;           // 12800
 constexpr int kRawStride = 41 * 1024;
 constexpr int kCopyBytes = kHalo * 2048;               // [18 rows][16 pixels][128 B]
 constexpr int kRingStageBytes = 16384;                 // [128 rows][128 B] weights, or one 16 x 8 pixel box of the skip source
@@ -112,7 +114,9 @@ __device__ __forceinline__ uint32_t act_pair_s(uint32_t raw, float a0, float b0,
 
 // ACT = false: the operand is x itself (16-bit, already in the weights' dtype) -- the stem convolution, which has no
 // GroupNorm in front of it (unet.py:55) but the same 3x3 structure; the transform is then a plain shifted copy.
-template <bool OUT_F16, bool kHead, bool PROF, bool ACT>
+// UP = true: `up` ResBlocks (nn.py:190-195) -- x is the HALF-resolution raw stream, the operand its activated nearest-2x
+// upsample: the 18 x 18 halo covers a 10 x 10 box of source pixels, each activated once and stored to its 2 x 2 positions.
+template <bool OUT_F16, bool kHead, bool PROF, bool ACT, bool UP>
 __global__ void __launch_bounds__(halo_s::kThreads, 1)
 conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW2,
@@ -217,8 +221,9 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         const int n0 = tile / tiles_img;
         for (int kc = 0; kc < p.kc1; ++kc, ++g) {
           mbar_wait(&raw_empty[0], (g & 1u) ^ 1u);
-          mbar_expect_tx(&raw_full[0], kRawBytes);
-          tma_load_4d(&tmRaw, &raw_full[0], raw_buf, kc * 64, w0 - 1, h0 - 1, n0);
+          mbar_expect_tx(&raw_full[0], UP ? kRawBytesUp : kRawBytes);
+          if (UP) tma_load_4d(&tmRaw, &raw_full[0], raw_buf, kc * 64, (w0 >> 1) - 1, (h0 >> 1) - 1, n0);
+          else tma_load_4d(&tmRaw, &raw_full[0], raw_buf, kc * 64, w0 - 1, h0 - 1, n0);
         }
       }
     } else if (warp == 18 && lane == 0) {
@@ -320,6 +325,106 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
     uint32_t g = 0;
     long long pf_raw = 0, pf_ae = 0, pf_work = 0, pf_t = 0;
     const long long pf_start = PROF ? clock64() : 0;
+    if constexpr (UP) {
+      // thread = (chunk j, source column lx, row phase lyq) owns the source pixels (lx, lyq + 3i), i < 4 (rows < 10); a source
+      // pixel (lx, ly) covers halo columns {2lx - 1, 2lx} and rows {2ly - 1, 2ly} (those inside the 18 x 18 halo)
+      const int lx = l36 % kUp, lyq = l36 / kUp;
+      const bool lane_on = l36 < 3 * kUp;
+      const int Hs = p.H >> 1, Ws = p.W >> 1;
+      uint32_t ro[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = (lyq + 3 * i) * kUp + lx;               // source pixel q of the TMA box sits at q * 128, swizzled by (q & 7)
+        ro[i] = raw_addr + q * 128 + ((j ^ (q & 7)) << 4);
+      }
+      uint32_t sb[2][3];
+      bool sv[2][3];
+#pragma unroll
+      for (int xk = 0; xk < 2; ++xk) {
+        const int xh = 2 * lx - 1 + xk;                       // halo column
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int xx = xh - s;
+          sv[xk][s] = lane_on && (unsigned)xh < (unsigned)kHalo && (unsigned)xx < 16u;
+          sb[xk][s] = copy_addr + s * kCopyBytes + (2 * lyq) * 2048 + ((xx >> 3) & 1) * 1024 + (xx & 7) * 128 + ((j ^ (xx & 7)) << 4);
+        }
+      }
+      for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
+        const int tile = wu / p.n_blocks;
+        const int w0 = (tile % p.tiles_w) * kT;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kT;
+        const int n0 = tile / tiles_img;
+        if (n0 != coef_n) {
+          named_bar_sync(7, kXfThreads);
+          const float4* src = reinterpret_cast<const float4*>(p.coef + (long long)n0 * p.ld_coef);
+          for (int i = tt; i < p.cin1 / 2; i += kXfThreads) {
+            const float4 t = __ldg(src + i);
+            const uint32_t ch = (uint32_t)i >> 2, off = ch * 64u + ((((uint32_t)i & 3u) + ((ch & 7u) >> 1)) & 3u) * 16u;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(coef_tab) + off), "f"(t.x), "f"(t.y),
+                         "f"(t.z), "f"(t.w) : "memory");
+          }
+          named_bar_sync(7, kXfThreads);
+          coef_n = n0;
+        }
+        // zero padding applies AFTER the activation: source pixels outside the (half-resolution) image stay 0
+        const int lw = (w0 >> 1) - 1 + lx, lh = (h0 >> 1) - 1 + lyq;
+        const bool col_ok = lane_on && (unsigned)lw < (unsigned)Ws;
+        for (int kc = 0; kc < p.kc1; ++kc, ++g) {
+          PF_T0();
+          mbar_wait(&raw_full[0], g & 1u);
+          PF_ADD(pf_raw);
+          PF_T0();
+          float4 c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[q].x), "=f"(c[q].y), "=f"(c[q].z), "=f"(c[q].w)
+                         : "r"(coef_s + (uint32_t)(kc * 512) + coef_q[q]));
+          }
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (col_ok && lyq + 3 * i < kUp && (unsigned)(lh + 3 * i) < (unsigned)Hs) {
+              uint32_t r1, r2, r3;
+              const uint32_t r0 = lds_u32x4(ro[i], r1, r2, r3);
+              v[i].x = act_pair_s<OUT_F16>(r0, c[0].x, c[0].y, c[0].z, c[0].w);
+              v[i].y = act_pair_s<OUT_F16>(r1, c[1].x, c[1].y, c[1].z, c[1].w);
+              v[i].z = act_pair_s<OUT_F16>(r2, c[2].x, c[2].y, c[2].z, c[2].w);
+              v[i].w = act_pair_s<OUT_F16>(r3, c[3].x, c[3].y, c[3].z, c[3].w);
+            }
+          }
+          PF_ADD(pf_work);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            PF_T0();
+            mbar_wait(&a_empty[s], (g & 1u) ^ 1u);
+            PF_ADD(pf_ae);
+#pragma unroll
+            for (int xk = 0; xk < 2; ++xk) {
+              if (sv[xk][s]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int ly = lyq + 3 * i;                         // source row of the box, 0..9
+                  if (ly < kUp) {
+                    if (ly >= 1) sts_u32x4(sb[xk][s] - 2048 + i * (6 * 2048), v[i]);     // halo row 2 ly - 1
+                    if (ly <= 8) sts_u32x4(sb[xk][s] + i * (6 * 2048), v[i]);            // halo row 2 ly
+                  }
+                }
+              }
+            }
+            if (s != 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (s == 0) mbar_arrive(&raw_empty[0]);
+                if (s == 2) mbar_arrive(&a_full[1]);
+                mbar_arrive(&a_full[s]);
+              }
+            }
+          }
+        }
+      }
+    } else {
     for (int wu = blockIdx.x; wu < total_units; wu += gridDim.x) {
       const int tile = wu / p.n_blocks;
       const int w0 = (tile % p.tiles_w) * kT;
@@ -404,6 +509,7 @@ conv_halo_swap_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_co
         }
       }
     }
+    }  // !UP
     if (PROF && p.prof && tt == 0) {
       unsigned long long* o = p.prof + 16 * blockIdx.x + 4;
       o[0] = (unsigned long long)(clock64() - pf_start); o[1] = pf_raw; o[2] = pf_ae; o[3] = pf_work;
@@ -530,7 +636,7 @@ bool conv_halo_swap_supported(const fidm_conv_args& a) {
   using namespace halo_s;
   if (!(a.ksize == 3 && a.stride == 1 && a.height % kT == 0 && a.width % kT == 0 && a.cin % 64 == 0 && a.cin > 0 &&
         a.cin <= kMaxCin)) return false;
-  if (a.x_half_res) return false;          // the up-sampling transform stays with K1h
+  if (a.x_half_res && (a.y_nchw_f32 || a.halo_copy)) return false;       // up-sampling transform: plain 128-wide layers only
   if (!(a.dtype == FIDM_F16 || a.dtype == FIDM_BF16)) return false;
   if (a.y_nchw_f32) return a.cout == 16 && !a.x2 && !a.residual && !a.colsum;
   return a.cout % 128 == 0;
@@ -542,7 +648,7 @@ bool conv_halo_swap_preferred(const fidm_conv_args& a) {
   return on && conv_halo_swap_supported(a) && (a.y_nchw_f32 || a.cout % 256 != 0);
 }
 
-template <bool OUT_F16, bool kHead, bool PROF = false, bool ACT = true>
+template <bool OUT_F16, bool kHead, bool PROF = false, bool ACT = true, bool UP = false>
 static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof = nullptr) {
   using namespace halo_s;
   ConvSwapParams p;
@@ -563,7 +669,11 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, uns
 
   CUtensorMap tmRaw, tmW, tmX2, tmW2;
   int rc;
-  if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHalo, kHalo, 1, 0))) return rc;
+  if (UP) {
+    if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width / 2, a.height / 2, a.batch, a.ld_x, kUp, kUp, 1, 0))) return rc;
+  } else {
+    if ((rc = make_nhwc_map(&tmRaw, a.x, a.cin, a.width, a.height, a.batch, a.ld_x, kHalo, kHalo, 1, 0))) return rc;
+  }
   if ((rc = make_matrix_map(&tmW, a.w, 9 * a.cin, a.cout, 9 * a.cin, kHead ? 16 : 128, OUT_F16 ? 1 : 0))) return rc;
   if (a.x2) {
     if ((rc = make_nhwc_map(&tmX2, a.x2, a.cin2, a.width, a.height, a.batch, a.ld_x2, kT, 8, 1, 0))) return rc;
@@ -572,11 +682,11 @@ static int launch_conv_halo_swap_t(const fidm_conv_args& a, cudaStream_t st, uns
     tmX2 = tmW; tmW2 = tmW;
   }
   static bool attr_set[kMaxDevices] = {};
-  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT>, kSmemBytes, attr_set));
+  FIDM_CUDA(ensure_dynamic_smem(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT, UP>, kSmemBytes, attr_set));
   const int units = p.tiles_w * p.tiles_h * p.B * p.n_blocks;
   const int sms = num_sms();
   const int grid = units < sms ? units : sms;
-  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
+  FIDM_CUDA(launch_pdl(conv_halo_swap_kernel<OUT_F16, kHead, PROF, ACT, UP>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmRaw, tmW, tmX2,
                        tmW2, p));
   FIDM_CHECK_LAUNCH("conv_halo_swap");
   return 0;
@@ -591,6 +701,8 @@ int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned lon
     FIDM_REQUIRE(!a.y_nchw_f32 && !a.gn_coef, FIDM_E_BADARG, "conv (halo copy): no head variant, no gn_coef");
     return f16 ? launch_conv_halo_swap_t<true, false, false, false>(a, st) : launch_conv_halo_swap_t<false, false, false, false>(a, st);
   }
+  if (a.x_half_res)
+    return f16 ? launch_conv_halo_swap_t<true, false, false, true, true>(a, st) : launch_conv_halo_swap_t<false, false, false, true, true>(a, st);
   if (prof && f16 && !a.y_nchw_f32) return launch_conv_halo_swap_t<true, false, true>(a, st, prof);   // instrumented (probe only)
   if (a.y_nchw_f32) return f16 ? launch_conv_halo_swap_t<true, true>(a, st) : launch_conv_halo_swap_t<false, true>(a, st);
   return f16 ? launch_conv_halo_swap_t<true, false>(a, st) : launch_conv_halo_swap_t<false, false>(a, st);

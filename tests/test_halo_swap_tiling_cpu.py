@@ -115,3 +115,47 @@ def test_skip_source_ring_alignment():
                     log.append(stage)
                     stage = (stage + 3) % stages
             assert all(s in (0, 1, 2) for s in log)
+
+
+def test_up_variant_source_box_covers_the_halo():
+    """K1s `up` variant: the 18x18 halo of the upsampled image is covered exactly once by the 10x10 source box at
+    ((w0>>1)-1, (h0>>1)-1): source pixel (lx, ly) -> halo columns {2lx-1, 2lx}, rows {2ly-1, 2ly}; 240 of the 288 transform
+    threads = (chunk j, lx, lyq) own source rows lyq + 3i < 10."""
+    g = torch.Generator().manual_seed(1)
+    Hs, Ws, C, Co = 16, 24, 3, 4
+    src = torch.randn(Hs, Ws, C, generator=g)
+    H, W = 2 * Hs, 2 * Ws
+    w = torch.randn(Co, 3, 3, C, generator=g)
+    out = torch.zeros(H, W, Co)
+    for h0 in range(0, H, T):
+        for w0 in range(0, W, T):
+            halo = torch.full((HALO, HALO, C), float("nan"))
+            for ly in range(10):
+                for lx in range(10):
+                    sh, sw = (h0 >> 1) - 1 + ly, (w0 >> 1) - 1 + lx
+                    v = src[sh, sw] if (0 <= sh < Hs and 0 <= sw < Ws) else torch.zeros(C)
+                    for y in (2 * ly - 1, 2 * ly):
+                        for x in (2 * lx - 1, 2 * lx):
+                            if 0 <= y < HALO and 0 <= x < HALO:
+                                assert torch.isnan(halo[y, x]).all()          # written exactly once
+                                halo[y, x] = v
+            assert not torch.isnan(halo).any()
+            cp = _copies(halo)
+            d = torch.zeros(Co, T * T)
+            for s in range(3):
+                for r in range(3):
+                    d += w[:, r, s, :] @ cp[s, r * T: r * T + T * T].T
+            out[h0:h0 + T, w0:w0 + T] = d.T.reshape(T, T, Co)
+    up = Fn.interpolate(src.permute(2, 0, 1)[None], scale_factor=2, mode="nearest")
+    want = Fn.conv2d(up, w.permute(0, 3, 1, 2), padding=1)[0].permute(1, 2, 0)
+    assert torch.allclose(out, want, atol=1e-4)
+    seen = []
+    for tt in range(288):
+        j, l36 = tt & 7, tt >> 3
+        lx, lyq = l36 % 10, l36 // 10
+        if l36 >= 30:
+            continue
+        for i in range(4):
+            if lyq + 3 * i < 10:
+                seen.append((j, lx, lyq + 3 * i))
+    assert len(seen) == len(set(seen)) == 8 * 100
