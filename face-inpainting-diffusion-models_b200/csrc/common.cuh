@@ -99,6 +99,22 @@ __device__ __forceinline__ void store_vec(T* p, const float (&in)[V]) {
   *reinterpret_cast<Vec<T, V>*>(p) = t;
 }
 
+// ---- division by a launch-time constant without the ~25-instruction I2F / MUFU.RCP sequence (the single-thread TMA
+// producers and MMA issuers of the tensor-core kernels are latency-bound on exactly that arithmetic):
+//   n / d == (umulhi(mul, n) + n) >> sh   for 0 <= n < 2^31,  sh = ceil(log2 d),  mul = floor(2^32 (2^sh - d) / d) + 1
+struct FastDiv { uint32_t d, mul, sh; };
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.sh = 0;
+  while ((1u << f.sh) < (uint32_t)d) ++f.sh;
+  f.mul = (uint32_t)((((unsigned long long)1 << 32) * ((1ull << f.sh) - (unsigned long long)d)) / (unsigned long long)d + 1ull);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return (int)((__umulhi(f.mul, (uint32_t)n) + (uint32_t)n) >> f.sh);
+}
+
 // ---- programmatic dependent launch (PDL), opt-in with FIDM_PDL=1.  The kernels of the UNet call pdl_wait() before their
 // first access to global memory that an earlier kernel may have written (or may still read), so they MAY be launched
 // with the programmatic-stream-serialization attribute: the launch, the block scheduling and the prologue (barrier

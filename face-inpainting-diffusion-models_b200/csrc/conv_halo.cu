@@ -737,6 +737,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constan
 
 // ------------------------------------------------------------------------------------------ host
 static unsigned long long* g_prof = nullptr;
+unsigned long long* conv_profile_buffer() { return g_prof; }
 
 bool conv_halo_supported(const fidm_conv_args& a) {
   return a.ksize == 3 && a.stride == 1 && a.height % halo::kTH == 0 && a.width % (2 * halo::kTW) == 0 &&

@@ -25,4 +25,7 @@ bool conv_halo_swap_supported(const fidm_conv_args& a);
 bool conv_halo_swap_preferred(const fidm_conv_args& a);     // supported AND the better kernel for this shape
 int launch_conv_halo_swap(const fidm_conv_args& a, cudaStream_t st, unsigned long long* prof = nullptr);
 
+// probe buffer set by fidm_conv_set_profile_buffer (null in production)
+unsigned long long* conv_profile_buffer();
+
 }  // namespace fidm

@@ -46,7 +46,21 @@ struct ConvTcParams {
   float* colsum; int colsum_slots; int cout;   // optional fused GroupNorm column sums
   int split_k;             // >1: the K loop of every tile is split over split_k CTAs (low-resolution layers)
   float* sk_ws; int* sk_cnt;   // fp32 partial tiles [tile][split][BLOCK_N][128], per-tile arrival counters
+  int cluster_split;           // 1: the split_k CTAs of a tile form a thread-block cluster (split_k in {2, 4, 8}, grid ==
+                               // units) and share the fold behind a cluster barrier; 0: arrival counter, last CTA folds
+  __nv_bfloat16* y_out; int ld_y;   // cluster_split: NHWC output written with plain 16-byte stores
+  int tw_sh, th_sh;            // log2 of TW, TH
+  FastDiv fd_split, fd_nblocks, fd_tw, fd_th, fd_kc1, fd_ks;   // divisors: split_k, n_blocks, tiles_w, tiles_h, kc1, ksize
+  unsigned long long* prof;    // probe only (tools/lowres_timeline.py): [CTA][32] globaltimer stamps of the first work unit
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(i) do { if (p.prof) p.prof[32 * blockIdx.x + (i)] = gtime_ns(); } while (0)
+#define TL1(i) do { if (p.prof && wu == unit) p.prof[32 * blockIdx.x + (i)] = gtime_ns(); } while (0)
 
 constexpr int kEpiWarps = 8;            // two warpgroups: chunk ch of a tile is drained by warpgroup (ch & 1)
 constexpr long long kSplitCounterBytes = 65536;
@@ -67,6 +81,70 @@ template <int BLOCK_N, int CG> struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 256 + 1024;
 };
 
+// Cluster split-K, second half: CTA `rank` of the cluster folds rows [rank * 128 / S, (rank + 1) * 128 / S) of the S
+// partial tiles (fp32 [BLOCK_N][128] column-major in the L2-resident workspace, made visible by the cluster barrier)
+// in split order -- the same fixed summation order whichever CTA does it -- and finishes them: + bias + emb + residual
+// -> bf16 -> 16-byte stores.  A thread owns 8 consecutive channels of one pixel; consecutive threads take consecutive
+// rows, so every load instruction of a warp reads whole 64/128-byte runs.  (The partials do NOT travel through
+// distributed shared memory: measured, 28 KB per CTA took 3-4 us that way, 5 B/clk -- tools/lowres_timeline.py.)
+template <int BLOCK_N, int S>
+__device__ __forceinline__ void cluster_fold_store(const ConvTcParams& p, const float* part, int rank, int tid, int co0,
+                                                   int w0, int h0, int n0) {
+  constexpr int kGroups = BLOCK_N / 8;              // 8-channel groups per row
+  constexpr int kRows = 128 / S;
+#pragma unroll 1
+  for (int g = tid; g < kRows * kGroups; g += kEpiWarps * 32) {
+    const int row = rank * kRows + g % kRows, c8 = g / kRows;
+    const float* rp = part + (c8 * 8) * 128 + row;
+    float v[S][8];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[s][j] = __ldcg(rp + s * (BLOCK_N * 128) + j * 128);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = v[0][j];
+#pragma unroll
+    for (int s = 1; s < S; ++s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += v[s][j];
+    const int wl = row & (p.TW - 1), hl = (row >> p.tw_sh) & (p.TH - 1), nl = row >> (p.tw_sh + p.th_sh);
+    const int n = n0 + nl;
+    if (n >= p.B) continue;                          // phantom rows of a tile that runs past the batch
+    const long long pix = ((long long)n * p.H + h0 + hl) * p.W + w0 + wl;
+    const int c = co0 + c8 * 8;
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (p.row_add) {
+      const float4* r4 = reinterpret_cast<const float4*>(p.row_add + (long long)n * p.ld_row_add + c);
+      const float4 b0 = __ldg(r4), b1 = __ldg(r4 + 1);
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (p.residual) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + c));
+      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        f[2 * q] += __uint_as_float(u[q] << 16);
+        f[2 * q + 1] += __uint_as_float(u[q] & 0xFFFF0000u);
+      }
+    }
+    uint4 pk;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 b1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 b3 = __floats2bfloat162_rn(f[6], f[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&b0);
+    pk.y = *reinterpret_cast<uint32_t*>(&b1);
+    pk.z = *reinterpret_cast<uint32_t*>(&b2);
+    pk.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(p.y_out + pix * p.ld_y + c) = pk;
+  }
+}
+
 template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -85,7 +163,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t* sk_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    TL(0);
+    if (p.prof) p.prof[32 * blockIdx.x + 14] = ((unsigned long long)gridDim.x << 32) | (BLOCK_N << 8) | p.split_k;
+  }
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // rank 0 = leader (issues the MMAs)
+  const bool csplit = CG == 1 && BLOCK_N >= 64 && p.cluster_split;  // cluster of split_k CTAs per tile, one unit per CTA
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile (CG=1) / tile-pair (CG=2) slot
   const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int taps = p.ksize * p.ksize;
@@ -117,6 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(1);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
   // nothing below may touch global memory before that kernel has completed.
   pdl_wait();
@@ -125,15 +209,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 8) {
     // ===================================================================== TMA producer
     if (lane == 0) {
+      TL(16);
       int stage = 0; uint32_t phase = 0;
+      const int main_iters = taps * p.kc1;
       for (int wu = unit; wu < total_tiles; wu += n_units) {
-        const int tile = wu / S, split = wu - tile * S;
-        const int it0 = (int)((long long)split * k_iters / S), it1 = (int)((long long)(split + 1) * k_iters / S);
-        const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
-        const int w0 = (m_blk % p.tiles_w) * p.TW;
-        const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
-        const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
+        const int tile = fdiv(wu, p.fd_split), split = wu - tile * S;
+        const int it0 = fdiv(split * k_iters, p.fd_split), it1 = fdiv((split + 1) * k_iters, p.fd_split);
+        const int tq = fdiv(tile, p.fd_nblocks);
+        const int n_blk = tile - tq * p.n_blocks, m_blk = tq * CG + (int)cta_rank;
+        const int mq = fdiv(m_blk, p.fd_tw), mq2 = fdiv(mq, p.fd_th);
+        const int w0 = (m_blk - mq * p.tiles_w) * p.TW;
+        const int h0 = (mq - mq2 * p.tiles_h) * p.TH;
+        const int n0 = mq2 * p.TN;
         const int co0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;   // this CTA's share of the weight tile
+        // The loop below is ONE thread's dependent instruction stream and paces the whole K loop when it is long (it was:
+        // two runtime divisions per iteration, ~630 cycles against 200-512 cycles of MMAs): the tap / channel-slice
+        // position is carried incrementally.
+        int kc64, cw, ch, wcol;                    // channel offset, input column / row of the box, weight-matrix column
+        {
+          const int itc = it0 < main_iters ? it0 : 0;
+          const int tap = fdiv(itc, p.fd_kc1), r = fdiv(tap, p.fd_ks);
+          kc64 = (itc - tap * p.kc1) * 64;
+          cw = w0 * p.stride + (tap - r * p.ksize) - pad;
+          ch = h0 * p.stride + r - pad;
+          wcol = itc * 64;                         // == tap * cin1 + kc * 64
+        }
+        const int cw_wrap = w0 * p.stride + p.ksize - pad;
+        TL1(17);
         for (int it = it0; it < it1; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -145,18 +247,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             mbar_arrive_cluster(&full_bar[stage], 0);
           }
-          if (it < taps * p.kc1) {
-            const int tap = it / p.kc1, kc = it - tap * p.kc1;
-            const int r = tap / p.ksize, s = tap - r * p.ksize;
+          if (it < main_iters) {
             if (CG == 1) {
-              tma_load_4d(&tmA, &full_bar[stage], sa, kc * 64, w0 * p.stride + s - pad, h0 * p.stride + r - pad, n0);
-              tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+              tma_load_4d(&tmA, &full_bar[stage], sa, kc64, cw, ch, n0);
+              tma_load_2d(&tmB, &full_bar[stage], sb, wcol, co0);
             } else {
-              tma_load_4d_2sm(&tmA, &full_bar[stage], sa, kc * 64, w0 * p.stride + s - pad, h0 * p.stride + r - pad, n0);
-              tma_load_2d_2sm(&tmB, &full_bar[stage], sb, tap * p.cin1 + kc * 64, co0);
+              tma_load_4d_2sm(&tmA, &full_bar[stage], sa, kc64, cw, ch, n0);
+              tma_load_2d_2sm(&tmB, &full_bar[stage], sb, wcol, co0);
+            }
+            kc64 += 64; wcol += 64;
+            if (kc64 == p.cin1) {                  // next tap
+              kc64 = 0;
+              if (++cw == cw_wrap) { cw -= p.ksize; ++ch; }
             }
           } else {
-            const int kc = it - taps * p.kc1;
+            const int kc = it - main_iters;
             if (CG == 1) {
               tma_load_4d(&tmA2, &full_bar[stage], sa, kc * 64, w0, h0, n0);
               tma_load_2d(&tmB2, &full_bar[stage], sb, kc * 64, co0);
@@ -165,8 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d_2sm(&tmB2, &full_bar[stage], sb, kc * 64, co0);
             }
           }
+          if (it == it0) TL1(2);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        TL1(3);
       }
     }
   } else if (warp == 9) {
@@ -179,14 +286,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int wu = unit; wu < total_tiles; wu += n_units) {
-        const int split = wu % S;
-        const int it0 = (int)((long long)split * k_iters / S), it1 = (int)((long long)(split + 1) * k_iters / S);
+        const int split = wu - fdiv(wu, p.fd_split) * S;
+        const int it0 = fdiv(split * k_iters, p.fd_split), it1 = fdiv((split + 1) * k_iters, p.fd_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int it = it0; it < it1; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == it0) TL1(4);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sa + kABytes);
@@ -201,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_2sm(&empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        TL1(5);
         // accumulator complete -> epilogue warps (of both CTAs)
         if (CG == 1) umma_commit(&tmem_full[acc]); else umma_commit_2sm(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -220,12 +329,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
     uint8_t* const stage_out = staging + wg * kStagingBytes;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int wu = unit; wu < total_tiles; wu += n_units) {
-      const int tile = wu / S, split = wu - tile * S;
-      const int n_blk = tile % p.n_blocks, m_blk = (tile / p.n_blocks) * CG + (int)cta_rank;
-      const int w0 = (m_blk % p.tiles_w) * p.TW;
-      const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.TH;
-      const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.TN;
+    if constexpr (CG == 1 && BLOCK_N >= 64) {
+      if (csplit) {
+        // ---- cluster split-K, first half: this CTA's fp32 partial tile -> the workspace ([column][row]: coalesced).
+        // Warpgroup wg drains the column half wg.  The fold comes after the role switch, behind the cluster barrier.
+        mbar_wait(&tmem_full[0], 0);
+        tc_fence_after();
+        if (threadIdx.x == 0) TL(6);
+        float* wsp = p.sk_ws + (long long)unit * (BLOCK_N * 128) + row;       // unit == tile * S + split
+#pragma unroll 1
+        for (int c = wg * (BLOCK_N / 2); c < (wg + 1) * (BLOCK_N / 2); c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)c, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(wsp + (c + j) * 128, __uint_as_float(v[j]));
+        }
+        tc_fence_before();
+        if (threadIdx.x == 0) TL(7);
+      }
+    }
+    for (int wu = unit; wu < total_tiles && !csplit; wu += n_units) {
+      const int tile = fdiv(wu, p.fd_split), split = wu - tile * S;
+      const int tq = fdiv(tile, p.fd_nblocks);
+      const int n_blk = tile - tq * p.n_blocks, m_blk = tq * CG + (int)cta_rank;
+      const int mq = fdiv(m_blk, p.fd_tw), mq2 = fdiv(mq, p.fd_th);
+      const int w0 = (m_blk - mq * p.tiles_w) * p.TW;
+      const int h0 = (mq - mq2 * p.tiles_h) * p.TH;
+      const int n0 = mq2 * p.TN;
       const int co0 = n_blk * BLOCK_N;
       const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
       const bool valid = n < p.B;
@@ -233,6 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (threadIdx.x == 0) TL1(6);
       const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(acc * BLOCK_N);
 
       if constexpr (BLOCK_N >= 64) {
@@ -258,6 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           __threadfence();
           named_bar_sync(5, kEpiWarps * 32);
+          if (threadIdx.x == 0) TL1(7);
           if (threadIdx.x == 0) {
             const int prev = atomicAdd(p.sk_cnt + tile, 1);
             const bool last = (prev == S - 1);
@@ -267,6 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           named_bar_sync(6, kEpiWarps * 32);
           finish = (*sk_flag != 0u);
           if (finish) __threadfence();
+          if (threadIdx.x == 0) { TL1(8); if (p.prof && wu == unit) p.prof[32 * blockIdx.x + 13] = finish ? 1 : 0; }
         }
         if (finish) {
         if (S == 1 && wg >= BLOCK_N / 64) {           // narrow tile: this warpgroup has no chunk, only releases TMEM
@@ -286,6 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 64; ++j) f[j] += __ldcg(rp + j * 128);
             }
+            if (threadIdx.x == 0 && ch == 0) TL1(9);
           } else {
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(t_acc + ch * 64, v0);
@@ -359,6 +494,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (issuer) {
               tma_store_4d(&tmY, stage_out, cbase, w0, h0, n0);
               bulk_commit_group();
+              if (threadIdx.x == 0) TL1(10);
             }
             if (p.colsum) {
               // Fused GroupNorm statistics: per-channel (sum, sum of squares) of the bf16 tile just staged.
@@ -414,10 +550,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) bulk_wait_group_read<0>();
+    if (threadIdx.x == 0) TL(11);
   }
 
+  if constexpr (CG == 1 && BLOCK_N >= 64) {
+    if (csplit) {
+      cluster_sync_all();                 // release / acquire at cluster scope: every partial of the tile is visible
+      if (threadIdx.x == 0) TL(8);
+      if (warp < kEpiWarps) {
+        const int rank = (int)cluster_ctarank();
+        const int tile = fdiv(unit, p.fd_split);
+        const int tq = fdiv(tile, p.fd_nblocks);
+        const int n_blk = tile - tq * p.n_blocks, m_blk = tq;
+        const int mq = fdiv(m_blk, p.fd_tw), mq2 = fdiv(mq, p.fd_th);
+        const int w0 = (m_blk - mq * p.tiles_w) * p.TW, h0 = (mq - mq2 * p.tiles_h) * p.TH, n0 = mq2 * p.TN;
+        const float* part = p.sk_ws + (long long)tile * S * (BLOCK_N * 128);
+        if (S == 2) cluster_fold_store<BLOCK_N, 2>(p, part, rank, (int)threadIdx.x, n_blk * BLOCK_N, w0, h0, n0);
+        else if (S == 4) cluster_fold_store<BLOCK_N, 4>(p, part, rank, (int)threadIdx.x, n_blk * BLOCK_N, w0, h0, n0);
+        else cluster_fold_store<BLOCK_N, 8>(p, part, rank, (int)threadIdx.x, n_blk * BLOCK_N, w0, h0, n0);
+      }
+      if (threadIdx.x == 0) TL(11);
+    }
+  }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) TL(12);
   if (warp == 9) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -497,11 +654,42 @@ int pick_pixel_box(int W, int H, int* tw, int* th, int* tn) {
   return 0;
 }
 
+// CTAs of conv_tc_kernel<BLOCK_N, 1> that can be co-resident when launched as clusters of S (a cluster needs S free
+// SMs inside one GPC), per device; 0 if the query fails.
+template <int BLOCK_N>
+static int cluster_capacity(int S) {
+  static int cache[kMaxDevices][9] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || S < 1 || S > 8) return 0;
+  if (cache[dev][S] == 0) {
+    using Cfg = ConvCfg<BLOCK_N, 1>;
+    static bool attr_set[kMaxDevices] = {};
+    if (ensure_dynamic_smem(conv_tc_kernel<BLOCK_N, 1>, Cfg::kSmemBytes, attr_set) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BLOCK_N, 1>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cache[dev][S] = n > 0 ? n * S : -1;
+  }
+  return cache[dev][S] > 0 ? cache[dev][S] : 0;
+}
+
+static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+// split_k > 1: the K loop of a tile is shared by split_k CTAs.  cluster_split: they are one thread-block cluster and
+// fold through distributed shared memory (split_k in {2, 4, 8}); otherwise through the global workspace.
 template <int BLOCK_N, int CG>
-static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k = 1) {
+static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k = 1, bool cluster_split = false) {
   using Cfg = ConvCfg<BLOCK_N, CG>;
   ConvTcParams p;
   p.split_k = split_k; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.cluster_split = cluster_split && split_k > 1 ? 1 : 0;
+  p.prof = conv_profile_buffer();
+  p.fd_split = make_fastdiv(split_k);
   const int Ho = a.height / a.stride, Wo = a.width / a.stride;          // a.height / a.width are the INPUT size
   p.B = a.batch; p.H = Ho; p.W = Wo; p.stride = a.stride;
   pick_pixel_box(Wo, Ho, &p.TW, &p.TH, &p.TN);
@@ -509,6 +697,8 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   p.tiles_w = Wo / p.TW; p.tiles_h = Ho / p.TH; p.tiles_n = (a.batch + p.TN - 1) / p.TN;
   p.n_blocks = a.cout / BLOCK_N;
   p.ksize = a.ksize; p.kc1 = a.cin / 64; p.cin1 = a.cin;
+  p.fd_nblocks = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
+  p.fd_kc1 = make_fastdiv(p.kc1); p.fd_ks = make_fastdiv(p.ksize);
   p.kc2 = a.x2 ? a.cin2 / 64 : 0;
   p.ab_f16 = a.dtype == FIDM_F16;
   const int f16 = p.ab_f16;
@@ -518,6 +708,12 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   p.cout_valid = a.cout_valid;
   p.colsum = a.colsum; p.cout = a.cout;
   p.colsum_slots = (p.TN == 1) ? p.tiles_w * p.tiles_h * 2 : 1;
+  p.y_out = reinterpret_cast<__nv_bfloat16*>(a.y); p.ld_y = a.ld_y;
+  p.tw_sh = log2_exact(p.TW); p.th_sh = log2_exact(p.TH);
+  if (p.cluster_split)
+    FIDM_REQUIRE(CG == 1 && BLOCK_N >= 64 && (split_k == 2 || split_k == 4 || split_k == 8) && !a.colsum && !a.y_nchw_f32 &&
+                     (uintptr_t)a.y % 16 == 0 && a.ld_y % 8 == 0,
+                 FIDM_E_BADARG, "conv_tc: cluster split-K needs a 64+ wide NHWC tile, split 2|4|8 and no fused statistics");
   if (a.colsum) FIDM_REQUIRE(!a.y_nchw_f32 && p.TN <= 2 && BLOCK_N >= 64, FIDM_E_SHAPE, "conv_tc: colsum not supported for this shape");
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmY;
@@ -544,16 +740,18 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
     // [tiles * split_k] fp32 partial tiles.
     const long long tiles = (long long)m_tiles * p.n_blocks;
     const long long need = kSplitCounterBytes + tiles * split_k * BLOCK_N * 128 * 4;
-    FIDM_REQUIRE(CG == 1 && BLOCK_N >= 64 && a.splitk_ws && a.splitk_ws_bytes >= need && tiles * 4 <= kSplitCounterBytes,
+    FIDM_REQUIRE(CG == 1 && BLOCK_N >= 64 && a.splitk_ws && a.splitk_ws_bytes >= need &&
+                     (p.cluster_split || tiles * 4 <= kSplitCounterBytes),
                  FIDM_E_BADARG, "conv_tc: split-K workspace too small (%lld needed)", need);
     p.sk_cnt = reinterpret_cast<int*>(a.splitk_ws);
     p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a.splitk_ws) + kSplitCounterBytes);
   }
   const int units = ((m_tiles + CG - 1) / CG) * p.n_blocks * split_k;  // (tile | tile pair) x K split
   const int slots = num_sms() / CG;
-  const int grid = (units < slots ? units : slots) * CG;
-  FIDM_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, CG, tmA, tmB, tmA2, tmB2,
-                       tmY, p));
+  // cluster split: one unit per CTA (clusters beyond the machine's capacity queue behind the first wave)
+  const int grid = p.cluster_split ? units : (units < slots ? units : slots) * CG;
+  FIDM_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st,
+                       p.cluster_split ? split_k : CG, tmA, tmB, tmA2, tmB2, tmY, p));
   FIDM_CHECK_LAUNCH("conv_tc");
   return 0;
 }
@@ -627,25 +825,47 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   // fold of the split partials by the last CTA of each tile.
   const int k_iters = a->ksize * a->ksize * (a->cin / 64) + (a->x2 ? a->cin2 / 64 : 0);
   static const bool split_ok = getenv("FIDM_CONV_SPLIT_K") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_K")) != 0;
+  // FIDM_CONV_SPLIT_CLUSTER=0: fold split partials through the global workspace (the round-1 path) instead of a cluster
+  static const bool cluster_ok = getenv("FIDM_CONV_SPLIT_CLUSTER") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_CLUSTER")) != 0;
+  const bool use_cluster = cluster_ok && !a->colsum && (uintptr_t)a->y % 16 == 0 && a->ld_y % 8 == 0;
   int best_n = 0, best_s = 1;
   double best = 1e30;
   const int ns[3] = {256, 128, 64};
-  const double mma_cyc[3] = {128.0, 72.0, 48.0};
   const int sms = num_sms();
   for (int i = 0; i < 3; ++i) {
     const int N = ns[i];
     if (a->cout % N) continue;
     const long long tiles = m_tiles * (a->cout / N);
     for (int S = 1; S <= 8; ++S) {
-      if (S > 1 && (!split_ok || !a->splitk_ws || k_iters / S < 6)) break;
-      if (S > 1 && (a->splitk_ws_bytes < kSplitCounterBytes + tiles * S * N * 128 * 4 || tiles * 4 > kSplitCounterBytes)) break;
-      const double waves = (double)((tiles * S + sms - 1) / sms);
-      const double compute = waves * ((double)k_iters / S) * 4.0 * mma_cyc[i];
+      if (S > 1 && (!split_ok || k_iters / S < 4)) break;
+      if (use_cluster && S != 1 && S != 2 && S != 4 && S != 8) continue;
+      if (S > 1 && (!a->splitk_ws || a->splitk_ws_bytes < kSplitCounterBytes + tiles * S * N * 128 * 4 ||
+                    (!use_cluster && tiles * 4 > kSplitCounterBytes)))
+        break;
+      // an SS-mode MMA with M = 128 streams its 128 A rows at one row per cycle whatever N is: a 64-deep K block costs
+      // 4 x 128 cycles on every tile width (tools/lowres_timeline.py: 270 ns per block for N = 64 ... 256)
+      int cap = sms;                                 // co-resident CTAs
+      if (use_cluster && S > 1) {
+        cap = N == 256 ? cluster_capacity<256>(S) : N == 128 ? cluster_capacity<128>(S) : cluster_capacity<64>(S);
+        if (cap <= 0) continue;
+      }
+      const double waves = (double)((tiles * S + cap - 1) / cap);
+      const double compute = waves * (double)((k_iters + S - 1) / S) * 512.0;
       const double traffic = (double)tiles * k_iters * (16384.0 + N * 128.0) / 12000.0;
-      const double fold = S > 1 ? (double)S * (N / 64) * 900.0 : 0.0;
-      const double cost = (compute > traffic ? compute : traffic) + fold + 3000.0;
+      const double fold = S == 1 ? 0.0 : use_cluster ? 2000.0 + 35.0 * N :      // park + barrier + shared fold, measured
+                          (double)S * (N / 64) * 900.0 + 4000.0;
+      const double epi = use_cluster && S > 1 ? 0.0 : (N / 64) * 600.0 * waves;
+      const double cost = (compute > traffic ? compute : traffic) + fold + epi + 3000.0;
       if (cost < best) { best = cost; best_n = N; best_s = S; }
     }
+  }
+  if (getenv("FIDM_CONV_TRACE"))
+    fprintf(stderr, "conv_tc: %dx%d B%d cin %d cout %d k%d -> N tile %d split %d %s (model %.0f cycles)\n", Ho, Wo, a->batch,
+            a->cin, a->cout, a->ksize, best_n, best_s, use_cluster && best_s > 1 ? "cluster" : "workspace", best);
+  if (use_cluster && best_s > 1) {
+    if (best_n == 256) return launch_conv_tc<256, 1>(*a, st, best_s, true);
+    if (best_n == 128) return launch_conv_tc<128, 1>(*a, st, best_s, true);
+    return launch_conv_tc<64, 1>(*a, st, best_s, true);
   }
   if (best_n == 256) return launch_conv_tc<256, 1>(*a, st, best_s);
   if (best_n == 128) return launch_conv_tc<128, 1>(*a, st, best_s);

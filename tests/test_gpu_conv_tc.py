@@ -178,6 +178,29 @@ def test_conv_tc_split_k_layers(cuda_lib, B, H, W, Cin, Cout, Cin2):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 512, 512), (3, 8, 8, 512, 256), (1, 16, 16, 512, 512), (8, 16, 16, 512, 512),
+                                            (1, 32, 32, 512, 512), (5, 8, 16, 1024, 1024), (8, 8, 8, 512, 512)])
+def test_conv_tc_split_k_cluster_epilogue(cuda_lib, B, H, W, Cin, Cout):
+    """The cluster split-K fold (partials exchanged through distributed shared memory, each CTA of the cluster finishing
+    128 / S rows of the tile): timestep-embedding rows, residual, and output into a channel slice of a wider concat
+    buffer whose other channels must stay untouched; odd batches leave phantom rows in the last tile."""
+    from fidm_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x, w, b, g = _mk(B, H, W, Cin, Cout, 3, seed=Cin + H + B)
+    wk = ops.repack_weight(w.float())
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g).bfloat16()
+    emb = torch.randn(B, Cout + 64, device="cuda", generator=g)[:, 64:]           # strided rows
+    buf = torch.full((B, H, W, Cout + 128), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = buf[..., 64:64 + Cout]
+    outs = []
+    for _ in range(2):
+        ops.conv2d(x, wk, b, row_add=emb, residual=res, out=out, impl="tc")
+        outs.append(out.clone())
+    _check(outs[0], _ref(x, w, b, row_add=emb, residual=res), "cluster split-K")
+    assert torch.equal(outs[0], outs[1])
+    assert (buf[..., :64] == 7.0).all() and (buf[..., 64 + Cout:] == 7.0).all()
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 64, 64, 128, 128), (3, 32, 48, 64, 256),
                                             (8, 256, 256, 128, 128), (2, 128, 128, 256, 256), (1, 8, 8, 512, 512)])
 def test_conv_tc_stride2(cuda_lib, B, H, W, Cin, Cout):
