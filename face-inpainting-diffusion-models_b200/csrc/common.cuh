@@ -118,17 +118,14 @@ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
 // ---- programmatic dependent launch (PDL), opt-in with FIDM_PDL=1.  The kernels of the UNet call pdl_wait() before their
 // first access to global memory that an earlier kernel may have written (or may still read), so they MAY be launched
 // with the programmatic-stream-serialization attribute: the launch, the block scheduling and the prologue (barrier
-// init, TMEM allocation, descriptor prefetch) then overlap the tail of the predecessor.  Measured inside the CUDA graph
-// of one evaluation it bought nothing (the graph's launch gaps are already ~1 us), so the attribute is off by default
-// and pdl_wait() is a no-op; pdl_trigger() (FIDM_PDL_TRIGGER) made things slower and compiles to nothing.
+// init, TMEM allocation, descriptor prefetch) then overlap the predecessor.  pdl_trigger() lets the successor launch
+// early ONLY when this grid is a single wave (every block resident: at most one per SM): round 1 measured that an
+// unconditional early trigger costs 1.5-6 % at batch 8, because the successor's blocks take SM resources from the
+// later waves of a multi-wave predecessor; a multi-wave grid keeps the implicit trigger at its completion.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#ifndef FIDM_PDL_TRIGGER
-#define FIDM_PDL_TRIGGER 0
-#endif
+constexpr unsigned kPdlSingleWaveBlocks = 148;       // B200: one block per SM
 __device__ __forceinline__ void pdl_trigger() {
-#if FIDM_PDL_TRIGGER
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
+  if (gridDim.x * gridDim.y * gridDim.z <= kPdlSingleWaveBlocks) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 bool pdl_enabled();          // FIDM_PDL=0 switches the attribute off (the device-side calls are then no-ops)
 

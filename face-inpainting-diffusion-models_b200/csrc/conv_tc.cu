@@ -84,64 +84,83 @@ template <int BLOCK_N, int CG> struct ConvCfg {
 // Cluster split-K, second half: CTA `rank` of the cluster folds rows [rank * 128 / S, (rank + 1) * 128 / S) of the S
 // partial tiles (fp32 [BLOCK_N][128] column-major in the L2-resident workspace, made visible by the cluster barrier)
 // in split order -- the same fixed summation order whichever CTA does it -- and finishes them: + bias + emb + residual
-// -> bf16 -> 16-byte stores.  A thread owns 8 consecutive channels of one pixel; consecutive threads take consecutive
-// rows, so every load instruction of a warp reads whole 64/128-byte runs.  (The partials do NOT travel through
-// distributed shared memory: measured, 28 KB per CTA took 3-4 us that way, 5 B/clk -- tools/lowres_timeline.py.)
+// -> bf16 -> 16-byte stores.  A thread owns 4 consecutive rows (pixels of one image row: TW >= 8) x 8 consecutive
+// channels: 8 float4 loads per split, up to 4 splits (32 loads) in flight, so the fold is one or two L2 round trips.
+// (The partials do NOT travel through distributed shared memory: measured, 28 KB per CTA took 3-4 us that way,
+// 5 B/clk -- tools/lowres_timeline.py.)
 template <int BLOCK_N, int S>
 __device__ __forceinline__ void cluster_fold_store(const ConvTcParams& p, const float* part, int rank, int tid, int co0,
                                                    int w0, int h0, int n0) {
+  constexpr int kQuads = 128 / S / 4;               // row quads of this CTA's slice
   constexpr int kGroups = BLOCK_N / 8;              // 8-channel groups per row
-  constexpr int kRows = 128 / S;
+  constexpr int SB = S < 4 ? S : 4;                 // splits loaded together
 #pragma unroll 1
-  for (int g = tid; g < kRows * kGroups; g += kEpiWarps * 32) {
-    const int row = rank * kRows + g % kRows, c8 = g / kRows;
+  for (int g = tid; g < kQuads * kGroups; g += kEpiWarps * 32) {
+    const int row = rank * (128 / S) + (g % kQuads) * 4, c8 = g / kQuads;
     const float* rp = part + (c8 * 8) * 128 + row;
-    float v[S][8];
+    float f[4][8];
 #pragma unroll
-    for (int s = 0; s < S; ++s)
+    for (int sb = 0; sb < S; sb += SB) {
+      float4 v[SB][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[s][j] = __ldcg(rp + s * (BLOCK_N * 128) + j * 128);
-    float f[8];
+      for (int s = 0; s < SB; ++s)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = v[0][j];
+        for (int j = 0; j < 8; ++j) v[s][j] = __ldcg(reinterpret_cast<const float4*>(rp + (sb + s) * (BLOCK_N * 128) + j * 128));
 #pragma unroll
-    for (int s = 1; s < S; ++s)
+      for (int s = 0; s < SB; ++s)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += v[s][j];
+        for (int j = 0; j < 8; ++j) {
+          if (sb == 0 && s == 0) { f[0][j] = v[s][j].x; f[1][j] = v[s][j].y; f[2][j] = v[s][j].z; f[3][j] = v[s][j].w; }
+          else { f[0][j] += v[s][j].x; f[1][j] += v[s][j].y; f[2][j] += v[s][j].z; f[3][j] += v[s][j].w; }
+        }
+    }
     const int wl = row & (p.TW - 1), hl = (row >> p.tw_sh) & (p.TH - 1), nl = row >> (p.tw_sh + p.th_sh);
     const int n = n0 + nl;
     if (n >= p.B) continue;                          // phantom rows of a tile that runs past the batch
-    const long long pix = ((long long)n * p.H + h0 + hl) * p.W + w0 + wl;
+    const long long pix = ((long long)n * p.H + h0 + hl) * p.W + w0 + wl;     // the quad's pixels are pix .. pix + 3
     const int c = co0 + c8 * 8;
+    float add[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (p.bias) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
-      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      add[0] += b0.x; add[1] += b0.y; add[2] += b0.z; add[3] += b0.w; add[4] += b1.x; add[5] += b1.y; add[6] += b1.z; add[7] += b1.w;
     }
     if (p.row_add) {
       const float4* r4 = reinterpret_cast<const float4*>(p.row_add + (long long)n * p.ld_row_add + c);
       const float4 b0 = __ldg(r4), b1 = __ldg(r4 + 1);
-      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-    }
-    if (p.residual) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + c));
-      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+      // (acc + bias) + emb, as the other epilogues add them
+      if (p.bias) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        f[2 * q] += __uint_as_float(u[q] << 16);
-        f[2 * q + 1] += __uint_as_float(u[q] & 0xFFFF0000u);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[q][j] += add[j];
       }
+      add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w; add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
     }
-    uint4 pk;
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
-    __nv_bfloat162 b1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]);
-    __nv_bfloat162 b3 = __floats2bfloat162_rn(f[6], f[7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&b0);
-    pk.y = *reinterpret_cast<uint32_t*>(&b1);
-    pk.z = *reinterpret_cast<uint32_t*>(&b2);
-    pk.w = *reinterpret_cast<uint32_t*>(&b3);
-    *reinterpret_cast<uint4*>(p.y_out + pix * p.ld_y + c) = pk;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[q][j] += add[j];
+      if (p.residual) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.residual + (pix + q) * p.ld_res + c));
+        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          f[q][2 * k] += __uint_as_float(u[k] << 16);
+          f[q][2 * k + 1] += __uint_as_float(u[k] & 0xFFFF0000u);
+        }
+      }
+      uint4 pk;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(f[q][0], f[q][1]);
+      __nv_bfloat162 b1 = __floats2bfloat162_rn(f[q][2], f[q][3]);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q][4], f[q][5]);
+      __nv_bfloat162 b3 = __floats2bfloat162_rn(f[q][6], f[q][7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&b0);
+      pk.y = *reinterpret_cast<uint32_t*>(&b1);
+      pk.z = *reinterpret_cast<uint32_t*>(&b2);
+      pk.w = *reinterpret_cast<uint32_t*>(&b3);
+      *reinterpret_cast<uint4*>(p.y_out + (pix + q) * p.ld_y + c) = pk;
+    }
   }
 }
 

@@ -642,51 +642,67 @@ extern "C" int fidm_groupnorm_silu_coeff(const fidm_gn_args* a, float* coef, int
 
 namespace fidm {
 // chansum[n][c0+c] = sum_{slot} colsum[n][slot][c]   (double accumulation, fixed order)
-constexpr int RS = 32;   // slices of the slot range per block (fixed summation tree: slice, then slices in order)
-__global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2* __restrict__ colsum, int slots, int C,
-                                                                   float2* __restrict__ chansum, int ld, int c0,
-                                                                   const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
+// A block owns CB channels of one image and cuts the slot range into RS = 1024 / CB slices (thread = channel x slice);
+// the summation tree is fixed: slots of a slice in order, slices strided by 8 in order, then the 8 partials in order.
+// CB = 8 gives a 256-channel batch-1 tensor 32 blocks instead of 8 (the kernel is a latency chain of L2 reads: more
+// blocks and 8 loads in flight per thread took it from 8 us to under 4).
+template <int CB>
+__global__ void __launch_bounds__(1024) gn_reduce_colsum_kernel(const float2* __restrict__ colsum, int slots, int C,
+                                                                float2* __restrict__ chansum, int ld, int c0,
+                                                                const fidm_gn_args a, float2* __restrict__ coef, int ld_coef) {
+  constexpr int RS = 1024 / CB;
   pdl_wait();
   pdl_trigger();
-  __shared__ double red[RS][32][2];
-  __shared__ double csum[32][2];
-  __shared__ float2 mr_s[32];
+  __shared__ double red[RS][CB][2];
+  __shared__ double red8[8][CB][2];
+  __shared__ double csum[CB][2];
+  __shared__ float2 mr_s[CB];
   const int n = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int j = threadIdx.x >> 5;
+  const int cl = threadIdx.x % CB;
+  const int c = blockIdx.x * CB + cl;
+  const int j = threadIdx.x / CB;
   double ds = 0.0, dss = 0.0;
   if (c < C) {
     const float2* q = colsum + (long long)n * slots * C + c;
     int s = j;
-    for (; s + 3 * RS < slots; s += 4 * RS) {
-      const float2 v0 = __ldcg(q + (long long)s * C), v1 = __ldcg(q + (long long)(s + RS) * C);
-      const float2 v2 = __ldcg(q + (long long)(s + 2 * RS) * C), v3 = __ldcg(q + (long long)(s + 3 * RS) * C);
-      ds += (double)v0.x; dss += (double)v0.y; ds += (double)v1.x; dss += (double)v1.y;
-      ds += (double)v2.x; dss += (double)v2.y; ds += (double)v3.x; dss += (double)v3.y;
+    for (; s + 7 * RS < slots; s += 8 * RS) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(q + (long long)(s + k * RS) * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { ds += (double)v[k].x; dss += (double)v[k].y; }
     }
     for (; s < slots; s += RS) {
       const float2 v = __ldcg(q + (long long)s * C);
       ds += (double)v.x; dss += (double)v.y;
     }
   }
-  red[j][threadIdx.x & 31][0] = ds;
-  red[j][threadIdx.x & 31][1] = dss;
+  red[j][cl][0] = ds;
+  red[j][cl][1] = dss;
+  __syncthreads();
+  if (j < 8) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll 4
+    for (int k = j; k < RS; k += 8) { sa += red[k][cl][0]; sb += red[k][cl][1]; }
+    red8[j][cl][0] = sa;
+    red8[j][cl][1] = sb;
+  }
   __syncthreads();
   if (j == 0) {
     double sa = 0.0, sb = 0.0;
 #pragma unroll
-    for (int k = 0; k < RS; ++k) { sa += red[k][threadIdx.x][0]; sb += red[k][threadIdx.x][1]; }
+    for (int k = 0; k < 8; ++k) { sa += red8[k][cl][0]; sb += red8[k][cl][1]; }
     // the consumer sees the sums rounded to fp32 (chansum): fold exactly those, as gn_coeff_kernel would
-    csum[threadIdx.x][0] = (double)(float)sa;
-    csum[threadIdx.x][1] = (double)(float)sb;
+    csum[cl][0] = (double)(float)sa;
+    csum[cl][1] = (double)(float)sb;
     if (c < C) chansum[(long long)n * ld + c0 + c] = make_float2((float)sa, (float)sb);
   }
   if (!coef) return;
   // Single-producer case: this tensor IS the GroupNorm input of the next conv (K1h), and every group lies inside one
-  // block's 32 channels: fold the groups here and write the coefficients -- no separate coefficient launch.
+  // block's CB channels: fold the groups here and write the coefficients -- no separate coefficient launch.
   __syncthreads();
   const int cpg = a.channels / a.groups;
-  const int gpb = 32 / cpg;                               // groups per block
+  const int gpb = CB / cpg;                               // groups per block
   if (threadIdx.x < gpb) {
     double gs = 0.0, gss = 0.0;
     for (int k = 0; k < cpg; ++k) { gs += csum[threadIdx.x * cpg + k][0]; gss += csum[threadIdx.x * cpg + k][1]; }
@@ -698,9 +714,27 @@ __global__ void __launch_bounds__(32 * RS) gn_reduce_colsum_kernel(const float2*
   }
   __syncthreads();
   if (j == 0 && c < C) {
-    const float2 mr = mr_s[threadIdx.x / cpg];
+    const float2 mr = mr_s[cl / cpg];
     coef[(long long)n * ld_coef + c] = gn_half_coeff(a, n, c, mr.x, mr.y);
   }
+}
+
+// channels per block: as few as the groups allow (cpg | CB) while the grid stays a sensible size
+static int reduce_colsum_cb(int channels, int batch, int cpg) {
+  const int cbs[3] = {8, 16, 32};
+  for (int i = 0; i < 3; ++i) {
+    const int cb = cbs[i];
+    if (cb < cpg || cb % cpg != 0) continue;
+    if ((long long)((channels + cb - 1) / cb) * batch <= 1024 || cb == 32) return cb;
+  }
+  return 32;
+}
+
+static void launch_reduce_colsum(int cb, dim3 grid, cudaStream_t st, const float2* colsum, int slots, int C, float2* chansum,
+                                 int ld, int c0, const fidm_gn_args& a, float2* coef, int ld_coef) {
+  if (cb == 8) launch_pdl(gn_reduce_colsum_kernel<8>, grid, dim3(1024), 0, st, 1, colsum, slots, C, chansum, ld, c0, a, coef, ld_coef);
+  else if (cb == 16) launch_pdl(gn_reduce_colsum_kernel<16>, grid, dim3(1024), 0, st, 1, colsum, slots, C, chansum, ld, c0, a, coef, ld_coef);
+  else launch_pdl(gn_reduce_colsum_kernel<32>, grid, dim3(1024), 0, st, 1, colsum, slots, C, chansum, ld, c0, a, coef, ld_coef);
 }
 }  // namespace fidm
 
@@ -709,10 +743,13 @@ extern "C" int fidm_groupnorm_reduce_colsum(const float* colsum, int32_t batch, 
   using namespace fidm;
   FIDM_REQUIRE(colsum && chansum && batch > 0 && slots > 0 && channels > 0 && c0 >= 0 && c0 + channels <= ld_chansum,
                FIDM_E_BADARG, "reduce_colsum: bad args");
-  dim3 grid((channels + 31) / 32, batch);
+  // the channel partition must not depend on who asks: the fused-coefficient entry below folds the same tensor and the
+  // two are required to agree bit for bit, so both derive CB from (channels, batch) and the usual 32 groups
+  const int cb = reduce_colsum_cb(channels, batch, channels % 32 == 0 && channels / 32 <= 32 ? channels / 32 : 32);
+  dim3 grid((channels + cb - 1) / cb, batch);
   fidm_gn_args none = {};
-  launch_pdl(gn_reduce_colsum_kernel, grid, dim3(32 * RS), 0, (cudaStream_t)stream, 1, reinterpret_cast<const float2*>(colsum),
-             slots, channels, reinterpret_cast<float2*>(chansum), ld_chansum, c0, none, (float2*)nullptr, 0);
+  launch_reduce_colsum(cb, grid, (cudaStream_t)stream, reinterpret_cast<const float2*>(colsum), slots, channels,
+                       reinterpret_cast<float2*>(chansum), ld_chansum, c0, none, (float2*)nullptr, 0);
   FIDM_CHECK_LAUNCH("reduce_colsum");
   return 0;
 }
@@ -729,9 +766,10 @@ extern "C" int fidm_groupnorm_reduce_colsum_coeff(const float* colsum, int32_t s
   FIDM_REQUIRE(cpg <= 32 && 32 % cpg == 0, FIDM_E_SHAPE, "reduce_colsum_coeff: %d channels per group do not tile 32", cpg);
   FIDM_REQUIRE(ld_coef >= a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_coef");
   if (a->scale_shift) FIDM_REQUIRE(a->ld_ss >= 2 * a->channels, FIDM_E_BADARG, "reduce_colsum_coeff: ld_ss < 2*channels");
-  dim3 grid(a->channels / 32, a->batch);
-  launch_pdl(gn_reduce_colsum_kernel, grid, dim3(32 * RS), 0, (cudaStream_t)stream, 1, reinterpret_cast<const float2*>(colsum),
-             slots, a->channels, reinterpret_cast<float2*>(chansum), ld_chansum, c0, *a, reinterpret_cast<float2*>(coef), ld_coef);
+  const int cb = reduce_colsum_cb(a->channels, a->batch, cpg);
+  dim3 grid(a->channels / cb, a->batch);
+  launch_reduce_colsum(cb, grid, (cudaStream_t)stream, reinterpret_cast<const float2*>(colsum), slots, a->channels,
+                       reinterpret_cast<float2*>(chansum), ld_chansum, c0, *a, reinterpret_cast<float2*>(coef), ld_coef);
   FIDM_CHECK_LAUNCH("reduce_colsum_coeff");
   return 0;
 }
