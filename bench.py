@@ -417,6 +417,12 @@ def run_sweep(args, preset, wl, model, fn, diffusion, dev, world, rank, local):
         tt = torch.full((b,), T // 2, device=dev)
         for _ in range(3):                                    # warm-up: plan build, graph capture, clocks
             fn(xin, tt, gt=gt, gt_keep_mask=keep)
+        # ... and the loop's own first-use costs (fused plan inputs, ping-pong buffers from a just-emptied allocator, K4):
+        # three steps of the same loop, untimed -- they were ~40 ms of a 190 ms batch-1 loop
+        for i, _ in enumerate(diffusion.ddim_sample_loop_progressive(fn, (b, 3, S, S), model_kwargs={"gt": gt, "gt_keep_mask": keep},
+                                                                     device=dev, eta=0.0, use_inpainting_injection=True)):
+            if i == 2:
+                break
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

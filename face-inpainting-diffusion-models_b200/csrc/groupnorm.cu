@@ -248,6 +248,17 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args 
       ss = fmaf(f1, f1, ss);
     }
   }
+  // the affine parameters do not depend on the statistics: their loads are issued here, under the reduction (the
+  // kernel is a chain of latencies -- tensor read, reduction, parameter read, write -- not a bandwidth problem)
+  const int c0 = g * cpg + jv * 8;
+  float ga[8], be[8], sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ga[i] = (active && a.gamma) ? __ldg(a.gamma + c0 + i) : 1.0f;
+    be[i] = (active && a.beta) ? __ldg(a.beta + c0 + i) : 0.0f;
+    sc[i] = (active && a.scale_shift) ? 1.0f + __ldg(a.scale_shift + (long long)n * a.ld_ss + c0 + i) : 1.0f;
+    sh[i] = (active && a.scale_shift) ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
+  }
   double ds = (double)s, dss = (double)ss;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -269,19 +280,14 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args 
   __syncthreads();
   if (!active) return;
   const float meanf = mr[0], rstd = mr[1];
-  const int c0 = g * cpg + jv * 8;
   float A[8], B[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float ga = a.gamma ? a.gamma[c0 + i] : 1.0f;
-    const float be = a.beta ? a.beta[c0 + i] : 0.0f;
-    float Ai = rstd * ga;
-    float Bi = be - meanf * Ai;
+    float Ai = rstd * ga[i];
+    float Bi = be[i] - meanf * Ai;
     if (a.scale_shift) {
-      const float sc = 1.0f + a.scale_shift[(long long)n * a.ld_ss + c0 + i];
-      const float sh = a.scale_shift[(long long)n * a.ld_ss + a.channels + c0 + i];
-      Ai *= sc;
-      Bi = Bi * sc + sh;
+      Ai *= sc[i];
+      Bi = Bi * sc[i] + sh[i];
     }
     A[i] = Ai;
     B[i] = Bi;
