@@ -214,11 +214,14 @@ __device__ __forceinline__ float silu_f(float v) {
 // pixel once into registers, reduces (sum, sum of squares) in a fixed tree, and writes the normalized / activated
 // values -- instead of a statistics launch plus an apply launch that reads the tensor twice.  Up to NV 16-byte vectors
 // per thread (NV * blockDim vectors per (image, group)).
-template <typename TY, int NV>
-__global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
+// MAXT = 1024 (NV = 8 only): twice the reach -- a 64x64 image of a 512-channel tensor (8192 vectors per group) at batch 1,
+// where the two-launch path costs 23 us and the machine is empty anyway; 64 registers per thread, so the affine
+// parameters are loaded after the reduction there.
+template <typename TY, int NV, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double red[16][2];
+  __shared__ double red[MAXT / 32][2];
   __shared__ float mr[2];
   constexpr bool FAST = true;
   const int g = blockIdx.x, n = blockIdx.y;
@@ -251,14 +254,18 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args 
   // the affine parameters do not depend on the statistics: their loads are issued here, under the reduction (the
   // kernel is a chain of latencies -- tensor read, reduction, parameter read, write -- not a bandwidth problem)
   const int c0 = g * cpg + jv * 8;
+  constexpr bool HOIST = MAXT <= 512;
   float ga[8], be[8], sc[8], sh[8];
+  auto load_affine = [&]() {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    ga[i] = (active && a.gamma) ? __ldg(a.gamma + c0 + i) : 1.0f;
-    be[i] = (active && a.beta) ? __ldg(a.beta + c0 + i) : 0.0f;
-    sc[i] = (active && a.scale_shift) ? 1.0f + __ldg(a.scale_shift + (long long)n * a.ld_ss + c0 + i) : 1.0f;
-    sh[i] = (active && a.scale_shift) ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
-  }
+    for (int i = 0; i < 8; ++i) {
+      ga[i] = (active && a.gamma) ? __ldg(a.gamma + c0 + i) : 1.0f;
+      be[i] = (active && a.beta) ? __ldg(a.beta + c0 + i) : 0.0f;
+      sc[i] = (active && a.scale_shift) ? 1.0f + __ldg(a.scale_shift + (long long)n * a.ld_ss + c0 + i) : 1.0f;
+      sh[i] = (active && a.scale_shift) ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
+    }
+  };
+  if (HOIST) load_affine();
   double ds = (double)s, dss = (double)ss;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -283,6 +290,12 @@ __global__ void __launch_bounds__(512) gn_fused_small_kernel(const fidm_gn_args 
   float A[8], B[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    if (!HOIST) {      // one channel's parameters at a time: 64 registers per thread
+      ga[i] = a.gamma ? __ldg(a.gamma + c0 + i) : 1.0f;
+      be[i] = a.beta ? __ldg(a.beta + c0 + i) : 0.0f;
+      sc[i] = a.scale_shift ? 1.0f + __ldg(a.scale_shift + (long long)n * a.ld_ss + c0 + i) : 1.0f;
+      sh[i] = a.scale_shift ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
+    }
     float Ai = rstd * ga[i];
     float Bi = be[i] - meanf * Ai;
     if (a.scale_shift) {
@@ -321,10 +334,16 @@ static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_
   if (a.ld_x % 8 || a.ld_y % 8 || (uintptr_t)a.x % 16 || (uintptr_t)a.y % 16) return false;
   const int vpp = cpg / 8;
   const long long total = (long long)a.height * a.width * vpp;
-  const int threads = total >= 512 ? 512 : (int)((total + 31) / 32) * 32;
+  int threads = total >= 512 ? 512 : (int)((total + 31) / 32) * 32;
   if (threads < vpp) return false;
-  const int stride = (threads / vpp) * vpp;
-  const long long per_thread = (total + stride - 1) / stride;
+  int stride = (threads / vpp) * vpp;
+  long long per_thread = (total + stride - 1) / stride;
+  // 1024-thread blocks only where the grid cannot fill the machine anyway (batch x groups blocks)
+  if (per_thread > 8 && a.batch * a.groups <= 64 && vpp <= 1024) {
+    threads = 1024;
+    stride = (threads / vpp) * vpp;
+    per_thread = (total + stride - 1) / stride;
+  }
   if (per_thread > 8) return false;    // 8 vectors (64 values) per thread stay in registers
   *vpp_o = vpp; *threads_o = threads; *stride_o = stride; *per_thread_o = (int)per_thread;
   return true;
@@ -335,7 +354,8 @@ static int try_gn_fused_small(const fidm_gn_args& a, cudaStream_t st) {
   int vpp, threads, stride, per_thread;
   if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread)) return -1;
   dim3 grid(a.groups, a.batch);
-  if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
+  if (threads > 512) launch_pdl(gn_fused_small_kernel<TY, 8, 1024>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
+  else if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   else launch_pdl(gn_fused_small_kernel<TY, 8>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   FIDM_CHECK_LAUNCH("groupnorm (fused small)");

@@ -67,6 +67,31 @@ def test_groupnorm_fp16_output(cuda_lib):
             assert torch.allclose(raw.float().permute(0, 3, 1, 2), wraw, atol=3e-2, rtol=1.6e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 512), (2, 64, 64, 512), (3, 64, 64, 512), (1, 64, 32, 1024), (1, 32, 32, 512)])
+def test_groupnorm_one_launch_small_batch(cuda_lib, B, H, W, C):
+    """Batch-1/2 tensors of 8192 vectors per (image, group) take the one-launch kernel with 1024-thread blocks (batch x
+    groups <= 64); batch 3 of the same shape keeps the two-launch path -- same numbers either way."""
+    import ctypes
+    from fidm_b200 import _lib as L
+    from fidm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + C)
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 2 + 0.3).bfloat16()
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C, device="cuda", generator=g)
+    ss = torch.randn(B, 2 * C, device="cuda", generator=g) * 0.3
+    a = L.GnArgs()
+    a.dtype, a.y_dtype = L.BF16, L.F16
+    a.batch, a.height, a.width, a.channels, a.groups = B, H, W, C, 32
+    a.ld_x = a.ld_y = C
+    a.x = a.y = L.ptr(x)                                           # only alignment is inspected
+    want_launches = 1 if (B * 32 <= 64 or H * W * (C // 32 // 8) <= 4096) else 2
+    assert cuda_lib.fidm_groupnorm_num_launches(ctypes.byref(a)) == want_launches
+    for use_ss in (False, True):
+        y = ops.groupnorm_silu(x, gamma, beta, scale_shift=ss if use_ss else None, silu=True, out_dtype=torch.float16)
+        wy, _ = _ref(x.float().permute(0, 3, 1, 2), gamma, beta, ss if use_ss else None, True, "none")
+        assert torch.allclose(y.float().permute(0, 3, 1, 2), wy, atol=3e-3, rtol=2e-3), use_ss
+
+
 def test_groupnorm_skip_norm_resample(cuda_lib):
     from fidm_b200 import ops
     x = torch.randn(2, 8, 8, 64, device="cuda")
