@@ -289,7 +289,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d_2sm(&tmB2, &full_bar[stage], sb, kc * 64, co0);
             }
           }
-          if (it == it0) TL1(2);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         TL1(3);
@@ -313,7 +312,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = it0; it < it1; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (it == it0) TL1(4);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sa + kABytes);

@@ -157,21 +157,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// distributed shared memory: 16-byte load from the same smem offset in CTA `cta` of the cluster
-__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t local_addr, uint32_t cta) {
-  float4 v;
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
-      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "r"(local_addr), "r"(cta)
-      : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_shared_f32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(

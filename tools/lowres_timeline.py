@@ -14,8 +14,10 @@ from fidm_b200 import _lib as L
 from fidm_b200 import ops
 
 dev = "cuda:0"
+# stamps 7 / 8: partial tile written to the workspace / past the cluster barrier (cluster split-K) or arrival counted
+# (FIDM_CONV_SPLIT_CLUSTER=0); 9 / 10 only exist on the workspace-fold and unsplit paths
 NAMES = ["entry", "setup done", "first TMA issued", "last TMA issued", "first stage full", "last MMA issued",
-         "accumulator ready", "partial parked", "arrival counted", "fold loaded", "TMA store issued", "epilogue done",
+         "accumulator ready", "partial parked", "barrier passed", "fold loaded", "TMA store issued", "epilogue done",
          "exit"]
 
 
@@ -53,8 +55,7 @@ def timeline(B, H, Cin, Cout, ks=3):
                 continue
             rel = (sel - t0).double() / 1e3
             print(f"   {nm:20s} min {rel.min():6.2f}  median {rel.median():6.2f}  max {rel.max():6.2f} us   (n={sel.numel()})")
-        for i, nm in ((16, "producer: past pdl_wait"), (17, "producer: indices"), (18, "producer: slot free"),
-                      (19, "producer: expect_tx"), (20, "producer: A issued")):
+        for i, nm in ((16, "producer: past pdl_wait"), (17, "producer: indices")):
             col = pr[:, i]
             rel = (col[col > 0] - t0).double() / 1e3
             if rel.numel():
