@@ -729,7 +729,7 @@ static int launch_conv_tc(const fidm_conv_args& a, cudaStream_t st, int split_k 
   p.tw_sh = log2_exact(p.TW); p.th_sh = log2_exact(p.TH);
   if (p.cluster_split)
     FIDM_REQUIRE(CG == 1 && BLOCK_N >= 64 && (split_k == 2 || split_k == 4 || split_k == 8) && !a.colsum && !a.y_nchw_f32 &&
-                     (uintptr_t)a.y % 16 == 0 && a.ld_y % 8 == 0,
+                     (uintptr_t)a.y % 16 == 0 && a.ld_y % 8 == 0 && p.TW >= 4,
                  FIDM_E_BADARG, "conv_tc: cluster split-K needs a 64+ wide NHWC tile, split 2|4|8 and no fused statistics");
   if (a.colsum) FIDM_REQUIRE(!a.y_nchw_f32 && p.TN <= 2 && BLOCK_N >= 64, FIDM_E_SHAPE, "conv_tc: colsum not supported for this shape");
 
@@ -844,7 +844,8 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   static const bool split_ok = getenv("FIDM_CONV_SPLIT_K") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_K")) != 0;
   // FIDM_CONV_SPLIT_CLUSTER=0: fold split partials through the global workspace (the round-1 path) instead of a cluster
   static const bool cluster_ok = getenv("FIDM_CONV_SPLIT_CLUSTER") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_CLUSTER")) != 0;
-  const bool use_cluster = cluster_ok && !a->colsum && (uintptr_t)a->y % 16 == 0 && a->ld_y % 8 == 0;
+  // (the shared fold hands a thread 4 consecutive pixels of one box row: TW >= 4)
+  const bool use_cluster = cluster_ok && !a->colsum && (uintptr_t)a->y % 16 == 0 && a->ld_y % 8 == 0 && tw >= 4;
   int best_n = 0, best_s = 1;
   double best = 1e30;
   const int ns[3] = {256, 128, 64};

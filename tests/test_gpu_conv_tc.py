@@ -179,11 +179,13 @@ def test_conv_tc_split_k_layers(cuda_lib, B, H, W, Cin, Cout, Cin2):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 512, 512), (3, 8, 8, 512, 256), (1, 16, 16, 512, 512), (8, 16, 16, 512, 512),
-                                            (1, 32, 32, 512, 512), (5, 8, 16, 1024, 1024), (8, 8, 8, 512, 512)])
+                                            (1, 32, 32, 512, 512), (5, 8, 16, 1024, 1024), (8, 8, 8, 512, 512),
+                                            (16, 6, 6, 512, 512), (40, 2, 2, 512, 256), (4, 12, 12, 512, 512)])
 def test_conv_tc_split_k_cluster_epilogue(cuda_lib, B, H, W, Cin, Cout):
-    """The cluster split-K fold (partials exchanged through distributed shared memory, each CTA of the cluster finishing
+    """The cluster split-K fold (partials parked in the workspace, one cluster barrier, each CTA of the cluster finishing
     128 / S rows of the tile): timestep-embedding rows, residual, and output into a channel slice of a wider concat
-    buffer whose other channels must stay untouched; odd batches leave phantom rows in the last tile."""
+    buffer whose other channels must stay untouched; odd batches leave phantom rows in the last tile.  Widths 6 and 2
+    give pixel boxes narrower than the fold's 4-pixel quads: those layers must take the workspace fold instead."""
     from fidm_b200 import ops
     torch.backends.cudnn.allow_tf32 = False
     x, w, b, g = _mk(B, H, W, Cin, Cout, 3, seed=Cin + H + B)
@@ -199,6 +201,42 @@ def test_conv_tc_split_k_cluster_epilogue(cuda_lib, B, H, W, Cin, Cout):
     _check(outs[0], _ref(x, w, b, row_add=emb, residual=res), "cluster split-K")
     assert torch.equal(outs[0], outs[1])
     assert (buf[..., :64] == 7.0).all() and (buf[..., 64 + Cout:] == 7.0).all()
+
+
+_WORKSPACE_FOLD_SCRIPT = r"""
+import math, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.nn.functional as Fn
+import fidm_b200
+from fidm_b200 import ops
+torch.backends.cudnn.allow_tf32 = False
+g = torch.Generator(device="cuda").manual_seed(5)
+for B, H, Cin, Cout in ((1, 8, 512, 512), (8, 8, 1024, 1024), (3, 16, 512, 512), (8, 16, 1024, 512)):
+    x = torch.randn(B, H, H, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Cin)).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, H, H, Cout, device="cuda", generator=g).bfloat16()
+    wk = ops.repack_weight(w.float())
+    ys = [ops.conv2d(x, wk, b, residual=res, impl="tc").clone() for _ in range(3)]
+    want = Fn.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1) + res.float().permute(0, 3, 1, 2)
+    got = ys[0].float().permute(0, 3, 1, 2)
+    rel = ((got - want).norm() / want.norm()).item()
+    assert rel < 4e-3, (B, H, Cin, Cout, rel)
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[1], ys[2])
+print("workspace fold ok")
+"""
+
+
+def test_conv_tc_workspace_fold_fallback(cuda_lib):
+    """FIDM_CONV_SPLIT_CLUSTER=0 keeps the round-1 split-K fold (arrival counter in the workspace, the last CTA of a tile
+    folds): still correct, bit-reproducible, counters re-armed.  The switch is read once per process -> subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FIDM_CONV_SPLIT_CLUSTER="0")
+    r = subprocess.run([sys.executable, "-c", _WORKSPACE_FOLD_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "workspace fold ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 64, 64, 128, 128), (3, 32, 48, 64, 256),
