@@ -214,17 +214,21 @@ __device__ __forceinline__ float silu_f(float v) {
 // pixel once into registers, reduces (sum, sum of squares) in a fixed tree, and writes the normalized / activated
 // values -- instead of a statistics launch plus an apply launch that reads the tensor twice.  Up to NV 16-byte vectors
 // per thread (NV * blockDim vectors per (image, group)).
-// MAXT = 1024 (NV = 8 only): twice the reach -- a 64x64 image of a 512-channel tensor (8192 vectors per group) at batch 1,
-// where the two-launch path costs 23 us and the machine is empty anyway; 64 registers per thread, so the affine
-// parameters are loaded after the reduction there.
-template <typename TY, int NV, int MAXT = 512>
-__global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
+// CS = 4: the (image, group) is shared by a thread-block CLUSTER of 4 blocks (block r owns vectors k = r*NV .. r*NV+NV-1
+// of every thread slot); the four (sum, sum of squares) partials are exchanged through distributed shared memory (32
+// bytes per block: the one place on this path where DSMEM's ~20 B/clk is plenty) and folded in rank order by every
+// block.  Used where batch x groups blocks cannot fill the machine (batch 1-2): 4x the blocks, 4x the reach (a 64x64
+// image of a 512-channel tensor, 8192 vectors per group, in one launch).
+template <typename TY, int NV, int CS = 1>
+__global__ void __launch_bounds__(512, 1) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double red[MAXT / 32][2];
+  __shared__ double red[16][2];
+  __shared__ __align__(16) double part[2];
   __shared__ float mr[2];
   constexpr bool FAST = true;
-  const int g = blockIdx.x, n = blockIdx.y;
+  const int rank = CS > 1 ? (int)(blockIdx.x % CS) : 0;          // == %cluster_ctarank (cluster dims (CS, 1, 1))
+  const int g = blockIdx.x / CS, n = blockIdx.y;
   const int hw = a.height * a.width;
   const int cpg = a.channels / a.groups;
   const int total = hw * vpp;                           // 16-byte vectors of this (image, group)
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_a
   float s = 0.0f, ss = 0.0f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int i = t + k * stride;
+    const int i = t + (rank * NV + k) * stride;
     v[k] = make_uint4(0u, 0u, 0u, 0u);
     if (active && i < total) v[k] = *reinterpret_cast<const uint4*>(xin + (long long)(i / vpp) * a.ld_x + jv * 8);
   }
@@ -254,7 +258,6 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_a
   // the affine parameters do not depend on the statistics: their loads are issued here, under the reduction (the
   // kernel is a chain of latencies -- tensor read, reduction, parameter read, write -- not a bandwidth problem)
   const int c0 = g * cpg + jv * 8;
-  constexpr bool HOIST = MAXT <= 512;
   float ga[8], be[8], sc[8], sh[8];
   auto load_affine = [&]() {
 #pragma unroll
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_a
       sh[i] = (active && a.scale_shift) ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
     }
   };
-  if (HOIST) load_affine();
+  load_affine();
   double ds = (double)s, dss = (double)ss;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -274,9 +277,34 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_a
   }
   if ((t & 31) == 0) { red[t >> 5][0] = ds; red[t >> 5][1] = dss; }
   __syncthreads();
+  if (CS > 1) {
+    if (t == 0) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a0 += red[k][0]; a1 += red[k][1]; }
+      part[0] = a0;
+      part[1] = a1;
+    }
+    // release / acquire at cluster scope: every block's partial is visible to its peers
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (t == 0) {
     double a0 = 0.0, a1 = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a0 += red[k][0]; a1 += red[k][1]; }
+    if (CS > 1) {
+      const uint32_t local = (uint32_t)__cvta_generic_to_shared(part);
+#pragma unroll
+      for (int r = 0; r < CS; ++r) {               // fixed order: identical statistics in all blocks of the cluster
+        double p0, p1;
+        asm volatile(
+            "{\n\t.reg .b32 ra;\n\t"
+            "mapa.shared::cluster.u32 ra, %2, %3;\n\t"
+            "ld.shared::cluster.v2.f64 {%0, %1}, [ra];\n\t}"
+            : "=d"(p0), "=d"(p1) : "r"(local), "r"(r) : "memory");
+        a0 += p0;
+        a1 += p1;
+      }
+    } else {
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a0 += red[k][0]; a1 += red[k][1]; }
+    }
     const double cnt = (double)cpg * hw;
     const double mean = a0 / cnt;
     double var = a1 / cnt - mean * mean;
@@ -285,48 +313,46 @@ __global__ void __launch_bounds__(MAXT, 1) gn_fused_small_kernel(const fidm_gn_a
     mr[1] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
   __syncthreads();
-  if (!active) return;
-  const float meanf = mr[0], rstd = mr[1];
-  float A[8], B[8];
+  if (active) {
+    const float meanf = mr[0], rstd = mr[1];
+    float A[8], B[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (!HOIST) {      // one channel's parameters at a time: 64 registers per thread
-      ga[i] = a.gamma ? __ldg(a.gamma + c0 + i) : 1.0f;
-      be[i] = a.beta ? __ldg(a.beta + c0 + i) : 0.0f;
-      sc[i] = a.scale_shift ? 1.0f + __ldg(a.scale_shift + (long long)n * a.ld_ss + c0 + i) : 1.0f;
-      sh[i] = a.scale_shift ? __ldg(a.scale_shift + (long long)n * a.ld_ss + a.channels + c0 + i) : 0.0f;
-    }
-    float Ai = rstd * ga[i];
-    float Bi = be[i] - meanf * Ai;
-    if (a.scale_shift) {
-      Ai *= sc[i];
-      Bi = Bi * sc[i] + sh[i];
-    }
-    A[i] = Ai;
-    B[i] = Bi;
-  }
-  TY* yo = reinterpret_cast<TY*>(a.y) + (long long)n * hw * a.ld_y + c0;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int i = t + k * stride;
-    if (i < total) {
-      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float y0 = fmaf(__uint_as_float(u[e] << 16), A[2 * e], B[2 * e]);
-        const float y1 = fmaf(__uint_as_float(u[e] & 0xFFFF0000u), A[2 * e + 1], B[2 * e + 1]);
-        f[2 * e] = a.silu ? silu_f<FAST>(y0) : y0;
-        f[2 * e + 1] = a.silu ? silu_f<FAST>(y1) : y1;
+    for (int i = 0; i < 8; ++i) {
+      float Ai = rstd * ga[i];
+      float Bi = be[i] - meanf * Ai;
+      if (a.scale_shift) {
+        Ai *= sc[i];
+        Bi = Bi * sc[i] + sh[i];
       }
-      store_vec<TY, 8>(yo + (long long)(i / vpp) * a.ld_y, f);
+      A[i] = Ai;
+      B[i] = Bi;
+    }
+    TY* yo = reinterpret_cast<TY*>(a.y) + (long long)n * hw * a.ld_y + c0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = t + (rank * NV + k) * stride;
+      if (i < total) {
+        const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y0 = fmaf(__uint_as_float(u[e] << 16), A[2 * e], B[2 * e]);
+          const float y1 = fmaf(__uint_as_float(u[e] & 0xFFFF0000u), A[2 * e + 1], B[2 * e + 1]);
+          f[2 * e] = a.silu ? silu_f<FAST>(y0) : y0;
+          f[2 * e + 1] = a.silu ? silu_f<FAST>(y1) : y1;
+        }
+        store_vec<TY, 8>(yo + (long long)(i / vpp) * a.ld_y, f);
+      }
     }
   }
+  // no block of the cluster may exit while a peer can still read its partial
+  if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // bf16 input, no resampling, no fused producer statistics, 16-byte aligned group slices, <= 8 * 512 vectors per
 // (image, group): the one-launch path.  Returns -1 when it does not apply.
-static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_o, int* stride_o, int* per_thread_o) {
+static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_o, int* stride_o, int* per_thread_o,
+                                int* cluster_o = nullptr) {
   static const bool enabled = getenv("FIDM_GN_FUSED_SMALL") == nullptr || atoi(getenv("FIDM_GN_FUSED_SMALL")) != 0;
   const int cpg = a.channels / a.groups;
   if (!enabled || a.dtype != FIDM_BF16 || (a.y_dtype != FIDM_BF16 && a.y_dtype != FIDM_F16)) return false;
@@ -334,27 +360,32 @@ static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_
   if (a.ld_x % 8 || a.ld_y % 8 || (uintptr_t)a.x % 16 || (uintptr_t)a.y % 16) return false;
   const int vpp = cpg / 8;
   const long long total = (long long)a.height * a.width * vpp;
-  int threads = total >= 512 ? 512 : (int)((total + 31) / 32) * 32;
+  const int threads = total >= 512 ? 512 : (int)((total + 31) / 32) * 32;
   if (threads < vpp) return false;
-  int stride = (threads / vpp) * vpp;
+  const int stride = (threads / vpp) * vpp;
   long long per_thread = (total + stride - 1) / stride;
-  // 1024-thread blocks only where the grid cannot fill the machine anyway (batch x groups blocks)
-  if (per_thread > 8 && a.batch * a.groups <= 64 && vpp <= 1024) {
-    threads = 1024;
-    stride = (threads / vpp) * vpp;
-    per_thread = (total + stride - 1) / stride;
+  // a 4-block cluster per (image, group) where batch x groups blocks cannot fill the machine and there is work to share
+  int cluster = 1;
+  if (a.batch * a.groups <= 64 && per_thread >= 4) {
+    cluster = 4;
+    per_thread = (per_thread + 3) / 4;
   }
   if (per_thread > 8) return false;    // 8 vectors (64 values) per thread stay in registers
   *vpp_o = vpp; *threads_o = threads; *stride_o = stride; *per_thread_o = (int)per_thread;
+  if (cluster_o) *cluster_o = cluster;
   return true;
 }
 
 template <typename TY>
 static int try_gn_fused_small(const fidm_gn_args& a, cudaStream_t st) {
-  int vpp, threads, stride, per_thread;
-  if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread)) return -1;
-  dim3 grid(a.groups, a.batch);
-  if (threads > 512) launch_pdl(gn_fused_small_kernel<TY, 8, 1024>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
+  int vpp, threads, stride, per_thread, cluster;
+  if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread, &cluster)) return -1;
+  dim3 grid(a.groups * cluster, a.batch);
+  if (cluster > 1) {
+    if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
+    else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
+    else launch_pdl(gn_fused_small_kernel<TY, 8, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
+  }
   else if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   else launch_pdl(gn_fused_small_kernel<TY, 8>, grid, dim3(threads), 0, st, 1, a, vpp, stride);

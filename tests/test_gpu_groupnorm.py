@@ -67,10 +67,12 @@ def test_groupnorm_fp16_output(cuda_lib):
             assert torch.allclose(raw.float().permute(0, 3, 1, 2), wraw, atol=3e-2, rtol=1.6e-2)
 
 
-@pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 512), (2, 64, 64, 512), (3, 64, 64, 512), (1, 64, 32, 1024), (1, 32, 32, 512)])
+@pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 512), (2, 64, 64, 512), (3, 64, 64, 512), (1, 64, 32, 1024), (1, 32, 32, 512), (1, 128, 128, 256),
+                                     (2, 24, 40, 256)])
 def test_groupnorm_one_launch_small_batch(cuda_lib, B, H, W, C):
-    """Batch-1/2 tensors of 8192 vectors per (image, group) take the one-launch kernel with 1024-thread blocks (batch x
-    groups <= 64); batch 3 of the same shape keeps the two-launch path -- same numbers either way."""
+    """Batch-1/2 tensors of 8192 vectors per (image, group) take the one-launch kernel as 4-block clusters (batch x
+    groups <= 64: the (sum, sum of squares) partials cross the cluster through distributed shared memory); batch 3 of the
+    same shape keeps the two-launch path -- same numbers either way."""
     import ctypes
     from fidm_b200 import _lib as L
     from fidm_b200 import ops
@@ -84,7 +86,7 @@ def test_groupnorm_one_launch_small_batch(cuda_lib, B, H, W, C):
     a.batch, a.height, a.width, a.channels, a.groups = B, H, W, C, 32
     a.ld_x = a.ld_y = C
     a.x = a.y = L.ptr(x)                                           # only alignment is inspected
-    want_launches = 1 if (B * 32 <= 64 or H * W * (C // 32 // 8) <= 4096) else 2
+    want_launches = 1 if (B * 32 <= 64 and H * W * (C // 32 // 8) <= 16384) or H * W * (C // 32 // 8) <= 4096 else 2
     assert cuda_lib.fidm_groupnorm_num_launches(ctypes.byref(a)) == want_launches
     for use_ss in (False, True):
         y = ops.groupnorm_silu(x, gamma, beta, scale_shift=ss if use_ss else None, silu=True, out_dtype=torch.float16)
