@@ -11,15 +11,21 @@
 //     64 bf16 with the 128-byte swizzle -- exactly the canonical K-major UMMA operand.  No im2col
 //     buffer ever exists.
 //   * The weight slice [BLOCK_N][64] for (tap, channel slice) is a 2-D TMA box of the KRSC matrix.
-//   * warp 4 = TMA producer, warp 5 = MMA issuer (one thread issues tcgen05.mma, accumulators live in
-//     TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
-//     warps 0-3 = epilogue: tcgen05.ld (one pixel row per thread) -> + bias[c] + emb[n][c]
-//     + residual -> bf16 -> swizzled smem -> TMA store (zero-copy into channel slices of concat
-//     buffers through the tensor map strides), or fp32 NCHW stores for the 6-channel head.
+//   * 320 threads: warps 0-7 = epilogue (two warpgroups), warp 8 = TMA producer, warp 9 = MMA issuer (one thread issues
+//     tcgen05.mma, accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+//     Epilogue: tcgen05.ld (one pixel row per thread) -> + bias[c] + emb[n][c] + residual -> bf16 -> swizzled smem ->
+//     TMA store (zero-copy into channel slices of concat buffers through the tensor map strides), or fp32 NCHW stores
+//     for the 6-channel head.
+//   * The producer and the MMA issuer are single threads: their loops carry the tap / channel-slice position
+//     incrementally and divide by launch constants with FastDiv (a runtime `/` in the producer loop paced every K loop
+//     at 330-430 ns per 64-deep block against 270 ns of MMAs; tools/lowres_timeline.py).
 //   * An optional second (activation, weight) pair is accumulated as extra K iterations: the 1x1
 //     skip_connection of channel-changing ResBlocks (nn.py:184,212) costs no extra pass.
 //   * Persistent CTAs (one per SM), static tile striding; tiles that share an M box are adjacent
 //     so their A boxes hit L2.
+//   * Low-resolution layers (few pixel tiles, deep K) split the K loop of a tile over the 2 / 4 / 8 CTAs of a
+//     thread-block cluster: partials parked in an L2-resident workspace, one cluster barrier, every CTA folds (split
+//     order: bit-reproducible) and finishes 128 / S rows -- cluster_fold_store below.
 #include <cuda.h>
 #include <stdlib.h>
 
