@@ -214,10 +214,10 @@ __device__ __forceinline__ float silu_f(float v) {
 // pixel once into registers, reduces (sum, sum of squares) in a fixed tree, and writes the normalized / activated
 // values -- instead of a statistics launch plus an apply launch that reads the tensor twice.  Up to NV 16-byte vectors
 // per thread (NV * blockDim vectors per (image, group)).
-// CS = 4: the (image, group) is shared by a thread-block CLUSTER of 4 blocks (block r owns vectors k = r*NV .. r*NV+NV-1
-// of every thread slot); the four (sum, sum of squares) partials are exchanged through distributed shared memory (32
-// bytes per block: the one place on this path where DSMEM's ~20 B/clk is plenty) and folded in rank order by every
-// block.  Used where batch x groups blocks cannot fill the machine (batch 1-2): 4x the blocks, 4x the reach (a 64x64
+// CS = 4 | 2: the (image, group) is shared by a thread-block CLUSTER of CS blocks (block r owns vectors k = r*NV ..
+// r*NV+NV-1 of every thread slot); the (sum, sum of squares) partials are exchanged through distributed shared memory
+// (16 bytes per block: the one place on this path where DSMEM's ~20 B/clk is plenty) and folded in rank order by every
+// block.  Used where batch x groups blocks cannot fill the machine (batch 1-2): CS x the blocks, CS x the reach (a 64x64
 // image of a 512-channel tensor, 8192 vectors per group, in one launch).
 template <typename TY, int NV, int CS = 1>
 __global__ void __launch_bounds__(512, 1) gn_fused_small_kernel(const fidm_gn_args a, int vpp, int stride) {
@@ -364,11 +364,16 @@ static bool gn_fused_small_plan(const fidm_gn_args& a, int* vpp_o, int* threads_
   if (threads < vpp) return false;
   const int stride = (threads / vpp) * vpp;
   long long per_thread = (total + stride - 1) / stride;
-  // a 4-block cluster per (image, group) where batch x groups blocks cannot fill the machine and there is work to share
+  // a 4- or 2-block cluster per (image, group) where the clustered grid is still one wave (one 512-thread block per SM)
+  // and a thread would otherwise hold more than 4 vectors -- measured at batch 1: 8 vectors per thread 8.8 us alone,
+  // 6.9 us as a cluster; <= 4 vectors 6.4 us alone, 6.9 us as a cluster; 8192 vectors per group 23 us in two launches,
+  // 8.3 us as a cluster (profiles/r2_launches_adm256_b1_summary.txt)
   int cluster = 1;
-  if (a.batch * a.groups <= 64 && per_thread >= 4) {
-    cluster = 4;
-    per_thread = (per_thread + 3) / 4;
+  if (per_thread > 4) {
+    const long long blocks = (long long)a.batch * a.groups;
+    if (blocks * 4 <= num_sms()) cluster = 4;
+    else if (blocks * 2 <= num_sms()) cluster = 2;
+    per_thread = (per_thread + cluster - 1) / cluster;
   }
   if (per_thread > 8) return false;    // 8 vectors (64 values) per thread stay in registers
   *vpp_o = vpp; *threads_o = threads; *stride_o = stride; *per_thread_o = (int)per_thread;
@@ -381,10 +386,13 @@ static int try_gn_fused_small(const fidm_gn_args& a, cudaStream_t st) {
   int vpp, threads, stride, per_thread, cluster;
   if (!gn_fused_small_plan(a, &vpp, &threads, &stride, &per_thread, &cluster)) return -1;
   dim3 grid(a.groups * cluster, a.batch);
-  if (cluster > 1) {
+  if (cluster == 4) {
     if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
     else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
     else launch_pdl(gn_fused_small_kernel<TY, 8, 4>, grid, dim3(threads), 0, st, 4, a, vpp, stride);
+  } else if (cluster == 2) {
+    if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4, 2>, grid, dim3(threads), 0, st, 2, a, vpp, stride);
+    else launch_pdl(gn_fused_small_kernel<TY, 8, 2>, grid, dim3(threads), 0, st, 2, a, vpp, stride);
   }
   else if (per_thread <= 2) launch_pdl(gn_fused_small_kernel<TY, 2>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
   else if (per_thread <= 4) launch_pdl(gn_fused_small_kernel<TY, 4>, grid, dim3(threads), 0, st, 1, a, vpp, stride);
