@@ -93,7 +93,9 @@ template <int BLOCK_N, int CG> struct ConvCfg {
 // -> bf16 -> 16-byte stores.  A thread owns 4 consecutive rows (pixels of one image row: TW >= 8) x 8 consecutive
 // channels: 8 float4 loads per split, up to 4 splits (32 loads) in flight, so the fold is one or two L2 round trips.
 // (The partials do NOT travel through distributed shared memory: measured, 28 KB per CTA took 3-4 us that way,
-// 5 B/clk -- tools/lowres_timeline.py.)
+// 5 B/clk -- tools/lowres_timeline.py.  Also measured and rejected: a [column quad][row][4] workspace layout with
+// 16-byte park stores and L1-cached fold loads -- the stores are issued 4x faster, but the cluster barrier then waits
+// that much longer for them to land and the fold's 16-byte cells at a 64-byte stride read slower: +0.5-0.9 us per launch.)
 template <int BLOCK_N, int S>
 __device__ __forceinline__ void cluster_fold_store(const ConvTcParams& p, const float* part, int rank, int tid, int co0,
                                                    int w0, int h0, int n0) {
