@@ -27,6 +27,7 @@
 //     thread-block cluster: partials parked in an L2-resident workspace, one cluster barrier, every CTA folds (split
 //     order: bit-reproducible) and finishes 128 / S rows -- cluster_fold_store below.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -883,6 +884,15 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
       const double epi = use_cluster && S > 1 ? 0.0 : (N / 64) * 600.0 * waves;
       const double cost = (compute > traffic ? compute : traffic) + fold + epi + 3000.0;
       if (cost < best) { best = cost; best_n = N; best_s = S; }
+    }
+  }
+  // FIDM_CONV_FORCE="N,S": tuning override (tools/conv_tune.py times every candidate against the model's pick)
+  if (const char* force = getenv("FIDM_CONV_FORCE")) {
+    int fn = 0, fs = 0;
+    if (sscanf(force, "%d,%d", &fn, &fs) == 2 && (fn == 64 || fn == 128 || fn == 256) && a->cout % fn == 0 && fs >= 1 && fs <= 8 &&
+        (fs == 1 || (k_iters / fs >= 1 && (!use_cluster || fs == 2 || fs == 4 || fs == 8) && a->splitk_ws &&
+                     a->splitk_ws_bytes >= kSplitCounterBytes + m_tiles * (a->cout / fn) * fs * fn * 128 * 4))) {
+      best_n = fn; best_s = fs;
     }
   }
   if (getenv("FIDM_CONV_TRACE"))
