@@ -846,9 +846,10 @@ extern "C" int fidm_conv2d_nhwc_bf16(const fidm_conv_args* a, fidm_stream_t stre
   if (a->cout % 256 == 0 && m_tiles * (a->cout / 256) >= want)
     return pair_ok ? launch_conv_tc<256, 2>(*a, st) : launch_conv_tc<256, 1>(*a, st);
   // Low-resolution layers (few pixel tiles, deep K).  Candidate (N tile, K split) pairs are scored with a small
-  // cost model in SM cycles: tensor time of one CTA's share, L2->SM operand traffic of the whole grid against the
-  // ~12 KB/clk the L2 delivers (measured: 442 MB in 62 us on the 16x16 layers) (these layers re-read the weights once per pixel tile), and the fixed-order
-  // fold of the split partials by the last CTA of each tile.
+  // cost model in SM cycles: tensor time of one CTA's share of the K loop, L2->SM operand traffic of the whole grid
+  // against the ~12 KB/clk the L2 delivers (measured: 442 MB in 62 us on the 16x16 layers; these layers re-read the
+  // weights once per pixel tile), and the fold of the split partials (shared by the cluster, or by the last CTA of a
+  // tile on the workspace path).  tools/conv_tune.py checks the pick against every forced candidate.
   const int k_iters = a->ksize * a->ksize * (a->cin / 64) + (a->x2 ? a->cin2 / 64 : 0);
   static const bool split_ok = getenv("FIDM_CONV_SPLIT_K") == nullptr || atoi(getenv("FIDM_CONV_SPLIT_K")) != 0;
   // FIDM_CONV_SPLIT_CLUSTER=0: fold split partials through the global workspace (the round-1 path) instead of a cluster
