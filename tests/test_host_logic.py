@@ -153,3 +153,26 @@ def test_topology_rejects_out_of_scope_arguments():
         F.UNetModel(64, 3, 64, 6, 1, (4,), dims=3)
     with pytest.raises(NotImplementedError):
         F.UNetModel(64, 3, 64, 6, 1, (4,), num_classes=10)
+
+
+@pytest.mark.parametrize("B,H,W,C,want", [
+    (8, 16, 16, 512, 1),      # 512 vectors per (image, group): the plain one-launch kernel
+    (8, 64, 64, 512, 2),      # 8192 vectors, 256 blocks: statistics + apply
+    (1, 64, 64, 512, 1),      # batch 1: a cluster of 4 blocks shares the (image, group)
+    (2, 64, 64, 512, 1),      # batch 2: clusters of 2 (the clustered grid must stay within one wave of 148 blocks)
+    (3, 64, 64, 512, 2),
+    (1, 128, 128, 256, 1),    # 16384 vectors per group: the reach of 4 blocks x 8 vectors per thread
+    (1, 256, 256, 256, 2),
+    (4, 8, 8, 96, 2),         # 3 channels per group: no 16-byte vectors
+])
+def test_groupnorm_launch_plan(B, H, W, C, want):
+    """fidm_groupnorm_num_launches is a planning query (no kernel runs): which GroupNorm path a tensor takes.  The
+    engine counts launches with it and the one-launch / cluster thresholds of csrc/groupnorm.cu are pinned here."""
+    lib = _lib.lib()
+    a = _lib.GnArgs()
+    a.dtype, a.y_dtype = _lib.BF16, _lib.F16
+    a.batch, a.height, a.width, a.channels, a.groups = B, H, W, C, 32
+    a.ld_x = a.ld_y = C
+    buf = ctypes.create_string_buffer(64)
+    a.x = a.y = ctypes.cast((ctypes.addressof(buf) + 15) // 16 * 16, ctypes.c_void_p)     # only alignment is inspected
+    assert lib.fidm_groupnorm_num_launches(ctypes.byref(a)) == want
