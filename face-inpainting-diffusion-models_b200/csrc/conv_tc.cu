@@ -66,6 +66,10 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// L1 prefetch of an epilogue operand (bias / emb / residual): the epilogues consume them group by group, each group a
+// dependent L2 round trip (~0.4 us) on the tail of a launch; prefetched while the accumulator / the partial tiles are
+// still in flight, the later loads hit L1.
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 #define TL(i) do { if (p.prof) p.prof[32 * blockIdx.x + (i)] = gtime_ns(); } while (0)
 #define TL1(i) do { if (p.prof && wu == unit) p.prof[32 * blockIdx.x + (i)] = gtime_ns(); } while (0)
 
@@ -106,6 +110,17 @@ __device__ __forceinline__ void cluster_fold_store(const ConvTcParams& p, const 
 #pragma unroll 1
   for (int g = tid; g < kQuads * kGroups; g += kEpiWarps * 32) {
     const int row = rank * (128 / S) + (g % kQuads) * 4, c8 = g / kQuads;
+    const int wl = row & (p.TW - 1), hl = (row >> p.tw_sh) & (p.TH - 1), nl = row >> (p.tw_sh + p.th_sh);
+    const int n = n0 + nl;
+    if (n >= p.B) continue;                          // phantom rows of a tile that runs past the batch
+    const long long pix = ((long long)n * p.H + h0 + hl) * p.W + w0 + wl;     // the quad's pixels are pix .. pix + 3
+    const int c = co0 + c8 * 8;
+    if (p.bias) prefetch_l1(p.bias + c);
+    if (p.row_add) prefetch_l1(p.row_add + (long long)n * p.ld_row_add + c);
+    if (p.residual) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prefetch_l1(p.residual + (pix + q) * p.ld_res + c);
+    }
     const float* rp = part + (c8 * 8) * 128 + row;
     float f[4][8];
 #pragma unroll
@@ -123,11 +138,6 @@ __device__ __forceinline__ void cluster_fold_store(const ConvTcParams& p, const 
           else { f[0][j] += v[s][j].x; f[1][j] += v[s][j].y; f[2][j] += v[s][j].z; f[3][j] += v[s][j].w; }
         }
     }
-    const int wl = row & (p.TW - 1), hl = (row >> p.tw_sh) & (p.TH - 1), nl = row >> (p.tw_sh + p.th_sh);
-    const int n = n0 + nl;
-    if (n >= p.B) continue;                          // phantom rows of a tile that runs past the batch
-    const long long pix = ((long long)n * p.H + h0 + hl) * p.W + w0 + wl;     // the quad's pixels are pix .. pix + 3
-    const int c = co0 + c8 * 8;
     float add[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (p.bias) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
@@ -388,6 +398,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = n < p.B;
       const long long pix = ((long long)n * p.H + h) * p.W + w;
 
+      if constexpr (BLOCK_N >= 64) {
+        if (valid) {
+#pragma unroll 1
+          for (int ch = wg; ch < BLOCK_N / 64; ch += 2) {
+            const int cbase = co0 + ch * 64;
+            if (p.bias) { prefetch_l1(p.bias + cbase); prefetch_l1(p.bias + cbase + 32); }
+            if (p.row_add) {
+              prefetch_l1(p.row_add + (long long)n * p.ld_row_add + cbase);
+              prefetch_l1(p.row_add + (long long)n * p.ld_row_add + cbase + 32);
+            }
+            if (p.residual) prefetch_l1(p.residual + pix * p.ld_res + cbase);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) TL1(6);
